@@ -1,0 +1,14 @@
+# Builds the product library (CUDA kernels + C ABI) for sm_100a, in-tree:
+#   odr_audioenc_b200/libtoolame_b200.so
+NVCC ?= nvcc
+SRC := odr_audioenc_b200/csrc
+OUT := odr_audioenc_b200/libtoolame_b200.so
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
+           -Xcompiler -fPIC,-Wall,-Wextra,-fvisibility=hidden -Xptxas -v
+HDRS := $(wildcard $(SRC)/*.h) include/toolame.h include/toolame_b200.h
+
+all: $(OUT)
+$(OUT): $(SRC)/mp2_kernels.cu $(SRC)/mp2_batch.cpp $(SRC)/toolame_shim.cpp $(HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC)/mp2_kernels.cu $(SRC)/mp2_batch.cpp $(SRC)/toolame_shim.cpp
+clean:
+	rm -f $(OUT)

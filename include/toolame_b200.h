@@ -1,0 +1,127 @@
+/*
+ * toolame_b200.h -- C ABI of the B200-native MPEG Layer II (MP2) DAB encode path.
+ *
+ * Two groups of entry points, all `extern "C"`, plain pointers and sizes:
+ *
+ *  (1) the libtoolame-dab API, unchanged (drop-in for the reference's
+ *      libtoolame-dab/toolame.h:13-48, export list libtoolame-dab.sym:1-9): the same nine
+ *      symbols with the same argument meaning, return convention and output chunking.  They are
+ *      declared in include/toolame.h (same prototypes as the reference header) and implemented on
+ *      top of group (2) with a one-frame batch per call.
+ *
+ *  (2) the batch API (new): encodes many frames of one stream per call, data-parallel over frames
+ *      and channels on the GPU.  It replaces N successive calls of toolame_encode_frame
+ *      (libtoolame-dab/toolame.c:267-554) and produces the same bytes, frame-aligned: frame n of
+ *      the output carries the ScF-CRC of frame n+1 (toolame.c:527-542), the last frame of the
+ *      stream its own.
+ *
+ * Every function returns 0 on success or a negative TLB_E_* code; nothing here calls exit()
+ * (the reference does for an illegal bitrate: common.c:110-115).  There is no CPU fallback: without a
+ * CUDA device tlb_batch_create fails with TLB_E_CUDA.
+ */
+#ifndef TOOLAME_B200_H
+#define TOOLAME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TLB_API __attribute__((visibility("default")))
+#else
+#define TLB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLB_E_PARAM   (-1)  /* illegal sample rate / mode / bitrate / psy model / pad length */
+#define TLB_E_CUDA    (-2)  /* CUDA runtime error (tlb_last_error() has the text) */
+#define TLB_E_ARG     (-3)  /* NULL pointer, bad sizes, bad history */
+#define TLB_E_UNSUPP  (-4)  /* legal for the reference, not (yet) built here (psy models 0, 2, 3; 44.1/22.05 kHz padding) */
+
+/* Stream parameters: what the reference takes through toolame_set_samplerate / _set_channel_mode /
+ * _set_bitrate / _set_psy_model / _set_pad (toolame.c:168-262). */
+typedef struct {
+    int32_t sample_rate;   /* Hz: 48000, 24000 (DAB); 32000 / 16000 also accepted */
+    int32_t channel_mode;  /* 's', 'd', 'j' or 'm' */
+    int32_t bitrate;       /* kbit/s, 0 = default of the reference (toolame.c:217-218) */
+    int32_t psy_model;     /* 1 (the odr-audioenc default) */
+    int32_t pad_len;       /* X-PAD + F-PAD bytes reserved per record, 0 = none (toolame_set_pad) */
+} tlb_config;
+
+/* Derived per-stream constants (common.c:76-93, availbits.c:37-67, encode_new.c:104-156). */
+typedef struct {
+    int32_t nch, lg_frame, sblimit, tablenum, dab_ext, version, bitrate_index, sfreq_idx;
+    int32_t samples_per_frame;  /* 1152 */
+    int32_t halo_samples;       /* PCM history a frame needs before its first sample (480) */
+} tlb_info;
+
+typedef struct tlb_batch tlb_batch;
+
+/* Create an encoder for one stream configuration on CUDA device `device`.
+ * max_chunk_frames = frames per kernel launch (0 = default); device working memory is
+ * about 20 kB per chunk frame and per in-flight chunk (two chunks are in flight). */
+TLB_API int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames);
+TLB_API void tlb_batch_destroy(tlb_batch *b);
+TLB_API int tlb_batch_info(const tlb_batch *b, tlb_info *info);
+TLB_API const char *tlb_last_error(void);
+
+/*
+ * Encode n_frames frames from HOST memory (host<->device copies included, chunks double-buffered).
+ *   pcm               interleaved s16 (WAV order), nch channels; pcm[0] = first sample of the first
+ *                     frame to encode
+ *   history_samples   samples per channel that are valid BEFORE pcm (pcm[-history_samples*nch ..]);
+ *                     0 = stream start (the reference's zero history), otherwise >= halo_samples
+ *   has_next          1: pcm holds n_frames+1 frames and frame n_frames only lends its ScF-CRC to
+ *                        the last emitted frame (a time chunk in the middle of a stream);
+ *                     0: stream end, the last frame keeps its own ScF-CRC
+ *   xpad              NULL, or n_frames+has_next records of pad_len+1 bytes in odr-audioenc's layout
+ *                     (src/odr-audioenc.cpp:823-852): data right-aligned in the first pad_len bytes,
+ *                     last byte = used length (0 or >= 2), i.e. what the caller passes to
+ *                     toolame_encode_frame as xpad_data / xpad_len
+ *   out               n_frames * lg_frame bytes
+ * pcm / out may be pageable or pinned (tlb_host_alloc); pinned memory makes the copies asynchronous.
+ */
+TLB_API int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples,
+                     int has_next, const uint8_t *xpad, uint8_t *out);
+
+/* Same, with pcm / xpad / out already in DEVICE memory of the encoder's GPU; d_pcm must be readable
+ * from d_pcm - history_samples*nch.  Asynchronous on the encoder's stream; tlb_batch_sync waits. */
+TLB_API int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames, size_t history_samples,
+                            int has_next, const uint8_t *d_xpad, uint8_t *d_out);
+TLB_API int tlb_batch_sync(tlb_batch *b);
+
+/* CUDA stream (cudaStream_t) the device-resident calls run on, for event timing by the caller. */
+TLB_API void *tlb_batch_stream(tlb_batch *b);
+/* Number of kernel launches issued by this encoder so far. */
+TLB_API uint64_t tlb_batch_launches(const tlb_batch *b);
+
+/* Pinned host memory for pcm / out buffers. */
+TLB_API void *tlb_host_alloc(size_t bytes);
+TLB_API void tlb_host_free(void *p);
+
+/* Per-frame intermediate results of the most recent chunk (parity tests read these; layouts below).
+ * Copies min(bytes, available) bytes and returns the number copied, or a negative error. */
+enum {
+    TLB_TAP_SB_SAMPLE = 0,  /* double [frames][nch][36][32]  subband samples (subband.c:201-310) */
+    TLB_TAP_SCALAR_PRE = 1, /* uint8  [frames][2][3][32]     scalefactor indices before the scfsi pattern */
+    TLB_TAP_J_SCALE = 2,    /* uint8  [frames][3][32]        joint-stereo scalefactor indices */
+    TLB_TAP_SMR = 3,        /* double [frames][2][32]        signal-to-mask ratios (psycho_1.c:568-581) */
+    TLB_TAP_SIDE = 4        /* tlb_side [frames] */
+};
+typedef struct {
+    uint8_t bit_alloc[2][32];
+    uint8_t scfsi[2][32];
+    uint8_t scalar[2][3][32];  /* after sf_transmission_pattern (encode_new.c:288-354) */
+    uint8_t scfcrc_own[4];     /* CRC_calcDAB of this frame, index = subband group (crc.c:58-98) */
+    uint8_t mode, mode_ext, jsbound, xpad_len;
+    int32_t adb_left;          /* zero-stuffing bits (toolame.c:509-512) */
+    uint32_t crc16;            /* crc.c:12-41 */
+} tlb_side;
+TLB_API long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,327 @@
+// mp2_batch.cpp -- host side of the batch encoder: stream configuration, chunking with PCM halos,
+// double-buffered host<->device copies, and the tlb_* C ABI (include/toolame_b200.h).
+//
+// Configuration rules restate what the reference derives in toolame_set_* (toolame.c:168-262), hdr_to_frps
+// (common.c:76-93), encode_init (encode_new.c:104-124) and available_bits (availbits.c:37-67).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "mp2_device.h"
+
+#define MP2_TABLE_QUAL [[maybe_unused]] static const
+#include "mp2_alloc_tables.h"
+#include "mp2_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(TLB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+constexpr int HALO = 512;         // samples of history staged per chunk (the filterbank needs 480, psy-1 192)
+constexpr int HALO_NEEDED = 480;
+constexpr size_t DEFAULT_CHUNK = 148 * 128; // frames per launch: a multiple of the SM count
+
+int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
+{
+    std::memset(&P, 0, sizeof P);
+    switch (c.sample_rate) { // ref: common.c:118-144
+    case 44100: P.version = 1; P.sfreq_idx = 0; break;
+    case 48000: P.version = 1; P.sfreq_idx = 1; break;
+    case 32000: P.version = 1; P.sfreq_idx = 2; break;
+    case 22050: P.version = 0; P.sfreq_idx = 0; break;
+    case 24000: P.version = 0; P.sfreq_idx = 1; break;
+    case 16000: P.version = 0; P.sfreq_idx = 2; break;
+    default: return fail(TLB_E_PARAM, "illegal sample rate");
+    }
+    if (c.psy_model < 0 || c.psy_model > 3) return fail(TLB_E_PARAM, "illegal psy model"); // ref: toolame.c:204
+    if (c.psy_model != 1) return fail(TLB_E_UNSUPP, "only psychoacoustic model 1 is built");
+    switch (c.channel_mode) { // ref: toolame.c:174-200
+    case 's': P.mode = 0; P.mode_ext = 0; break;
+    case 'j': P.mode = 1; P.mode_ext = 2; break;
+    case 'd': P.mode = 2; P.mode_ext = 0; break;
+    case 'm': P.mode = 3; P.mode_ext = 0; break;
+    default: return fail(TLB_E_PARAM, "illegal channel mode");
+    }
+    P.nch = P.mode == 3 ? 1 : 2;
+    int kbps = c.bitrate ? c.bitrate : MP2_BITRATE[P.version][10]; // ref: toolame.c:217-218
+    P.bitrate_index = -1;
+    for (int i = 0; i < 15; i++) // ref: common.c:95-116
+        if (MP2_BITRATE[P.version][i] == kbps) { P.bitrate_index = i; break; }
+    if (P.bitrate_index < 0) return fail(TLB_E_PARAM, "illegal bitrate for this sample rate");
+    P.dab_ext = 4; // ref: toolame.c:147,225-232
+    if (P.version == 1 && kbps / (P.mode == 3 ? 1 : 2) < 56) P.dab_ext = 2;
+    if (c.pad_len < 0 || c.pad_len > 255) return fail(TLB_E_PARAM, "illegal pad length");
+    P.pad_len = c.pad_len;
+    const int per_ch = kbps / P.nch;
+    static const int sfreq_khz_int[2][3] = {{22, 24, 16}, {44, 48, 32}};
+    const int sfrq = sfreq_khz_int[P.version][P.sfreq_idx];
+    if (P.version == 1) { // ref: encode_new.c:112-121 == tables.c:24-36
+        if ((sfrq == 48 && per_ch >= 56) || (per_ch >= 56 && per_ch <= 80)) P.tablenum = 0;
+        else if (sfrq != 48 && per_ch >= 96) P.tablenum = 1;
+        else if (sfrq != 32 && per_ch <= 48) P.tablenum = 2;
+        else P.tablenum = 3;
+    } else P.tablenum = 4;
+    P.sblimit = MP2_TAB_SBLIMIT[P.tablenum];
+    {   // ref: availbits.c:42-46; the padding branch (non-integral slot count) only exists at 44.1 / 22.05 kHz
+        static const double s_freq[2][3] = {{22.05, 24, 16}, {44.1, 48, 32}};
+        const double average = (1152.0 / s_freq[P.version][P.sfreq_idx]) * ((double)kbps / 8.0);
+        P.lg_frame = (int)average;
+        if (average - (double)P.lg_frame != 0) return fail(TLB_E_UNSUPP, "sample rates that need padding slots are not built");
+    }
+    if (P.lg_frame % 4 || P.lg_frame > 1728) return fail(TLB_E_UNSUPP, "frame length");
+    P.jsbound = P.mode == 1 ? MP2_JSBOUND[P.mode_ext] : P.sblimit; // ref: common.c:87-91
+    P.psy_freq = P.version == 1 ? P.sfreq_idx : P.sfreq_idx + 4;   // ref: psycho_1.c:42-48
+    P.sub_size = MP2_SUB_SIZE[P.psy_freq];
+    P.cb_count = MP2_CB_COUNT[P.psy_freq];
+    P.bitrate_per_ch = per_ch;
+    I.nch = P.nch; I.lg_frame = P.lg_frame; I.sblimit = P.sblimit; I.tablenum = P.tablenum; I.dab_ext = P.dab_ext;
+    I.version = P.version; I.bitrate_index = P.bitrate_index; I.sfreq_idx = P.sfreq_idx;
+    I.samples_per_frame = 1152; I.halo_samples = HALO_NEEDED;
+    return 0;
+}
+
+struct Slot {
+    int16_t *d_pcm = nullptr;   // HALO*nch + (chunk+1)*1152*nch samples
+    uint8_t *d_xpad = nullptr;
+    uint8_t *d_out = nullptr;
+    double *sb = nullptr;
+    uint8_t *scalar_pre = nullptr, *j_scale = nullptr;
+    double *smr = nullptr;
+    tlb_side *side = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    int last_fa = 0;
+};
+
+} // namespace
+
+struct tlb_batch {
+    tlb_config cfg;
+    Mp2Params P;
+    tlb_info info;
+    int device = 0;
+    size_t chunk = 0;
+    Slot slot[2];
+    uint8_t *d_map = nullptr;
+    uint64_t launches = 0;
+    int last_slot = 0;
+};
+
+namespace {
+
+int alloc_slot(tlb_batch *b, Slot &s)
+{
+    const size_t fa = b->chunk + 1, nch = (size_t)b->P.nch;
+    CU(cudaMalloc(&s.d_pcm, (HALO + fa * 1152) * nch * sizeof(int16_t)));
+    CU(cudaMalloc(&s.d_xpad, fa * (size_t)(b->P.pad_len + 1)));
+    CU(cudaMalloc(&s.d_out, b->chunk * (size_t)b->P.lg_frame));
+    CU(cudaMalloc(&s.sb, fa * nch * 1152 * sizeof(double)));
+    CU(cudaMalloc(&s.scalar_pre, fa * 192));
+    CU(cudaMalloc(&s.j_scale, fa * 96));
+    CU(cudaMalloc(&s.smr, fa * 64 * sizeof(double)));
+    CU(cudaMalloc(&s.side, fa * sizeof(tlb_side)));
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return 0;
+}
+
+void free_slot(Slot &s)
+{
+    cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
+    cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    s = Slot();
+}
+
+Mp2Chunk chunk_of(const tlb_batch *b, const Slot &s, const int16_t *pcm, long lo, const uint8_t *xpad, uint8_t *out,
+                  int fa, int n_out)
+{
+    (void)b;
+    Mp2Chunk c;
+    c.pcm = pcm; c.lo = lo; c.xpad = xpad; c.sb = s.sb; c.scalar_pre = s.scalar_pre; c.j_scale = s.j_scale;
+    c.smr = s.smr; c.side = s.side; c.out = out; c.fa = fa; c.n_out = n_out;
+    return c;
+}
+
+int check_args(const tlb_batch *b, const void *pcm, size_t history, const void *out)
+{
+    if (!b || !pcm || !out) return fail(TLB_E_ARG, "NULL argument");
+    if (history != 0 && history < (size_t)HALO_NEEDED) return fail(TLB_E_ARG, "history_samples must be 0 or >= 480");
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *tlb_last_error(void) { return g_err.c_str(); }
+
+int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames)
+{
+    if (!out || !cfg) return fail(TLB_E_ARG, "NULL argument");
+    *out = nullptr;
+    Mp2Params P;
+    tlb_info I;
+    int rc = configure(*cfg, P, I);
+    if (rc) return rc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(TLB_E_CUDA, "no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= n_dev) return fail(TLB_E_ARG, "bad device index");
+    CU(cudaSetDevice(device));
+    tlb_batch *b = new (std::nothrow) tlb_batch();
+    if (!b) return fail(TLB_E_ARG, "out of memory");
+    b->cfg = *cfg; b->P = P; b->info = I; b->device = device;
+    b->chunk = max_chunk_frames ? max_chunk_frames : DEFAULT_CHUNK;
+    for (int i = 0; i < 2; i++)
+        if ((rc = alloc_slot(b, b->slot[i]))) { tlb_batch_destroy(b); return rc; }
+    {   // FFT line -> threshold-table partition (ref: psycho_1.c:160-168); lines above the last partition keep the
+        // allocator's zero (mem.c:21)
+        uint8_t map[512];
+        std::memset(map, 0, sizeof map);
+        for (int i = 1; i < P.sub_size; i++)
+            for (int j = MP2_LTG_LINE[P.psy_freq][i - 1]; j <= MP2_LTG_LINE[P.psy_freq][i]; j++) map[j] = (uint8_t)i;
+        if (cudaMalloc(&b->d_map, 512) != cudaSuccess ||
+            cudaMemcpy(b->d_map, map, 512, cudaMemcpyHostToDevice) != cudaSuccess) {
+            tlb_batch_destroy(b);
+            return fail(TLB_E_CUDA, "map upload failed");
+        }
+    }
+    *out = b;
+    return 0;
+}
+
+void tlb_batch_destroy(tlb_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (auto &s : b->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        free_slot(s);
+    }
+    cudaFree(b->d_map);
+    delete b;
+}
+
+int tlb_batch_info(const tlb_batch *b, tlb_info *info)
+{
+    if (!b || !info) return fail(TLB_E_ARG, "NULL argument");
+    *info = b->info;
+    return 0;
+}
+
+void *tlb_batch_stream(tlb_batch *b) { return b ? (void *)b->slot[0].stream : nullptr; }
+uint64_t tlb_batch_launches(const tlb_batch *b) { return b ? b->launches : 0; }
+
+int tlb_batch_sync(tlb_batch *b)
+{
+    if (!b) return fail(TLB_E_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    for (auto &s : b->slot) CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples, int has_next,
+                     const uint8_t *xpad, uint8_t *out)
+{
+    int rc = check_args(b, pcm, history_samples, out);
+    if (rc) return rc;
+    CU(cudaSetDevice(b->device));
+    const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
+    const bool use_xpad = xpad && b->P.pad_len;
+    size_t k = 0;
+    for (size_t f0 = 0; f0 < n_frames; f0 += b->chunk, k++) {
+        Slot &s = b->slot[k & 1];
+        const size_t n_out = std::min(b->chunk, n_frames - f0);
+        const bool next_here = f0 + n_out < n_frames || has_next;
+        const size_t fa = n_out + (next_here ? 1 : 0);
+        const size_t hist = std::min<size_t>(HALO, f0 * 1152 + history_samples);
+        // (stream order makes re-use of the slot's buffers safe: the copies below queue behind its previous chunk)
+        CU(cudaMemcpyAsync(s.d_pcm + (HALO - hist) * nch, pcm + (f0 * 1152 - hist) * nch,
+                           (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
+        if (use_xpad) CU(cudaMemcpyAsync(s.d_xpad, xpad + f0 * rec, fa * rec, cudaMemcpyHostToDevice, s.stream));
+        Mp2Chunk c = chunk_of(b, s, s.d_pcm + HALO * nch, -(long)hist, use_xpad ? s.d_xpad : nullptr, s.d_out, (int)fa, (int)n_out);
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + f0 * lg, s.d_out, n_out * lg, cudaMemcpyDeviceToHost, s.stream));
+        s.last_fa = (int)fa;
+        b->last_slot = (int)(k & 1);
+    }
+    for (auto &s : b->slot) CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames, size_t history_samples, int has_next,
+                            const uint8_t *d_xpad, uint8_t *d_out)
+{
+    int rc = check_args(b, d_pcm, history_samples, d_out);
+    if (rc) return rc;
+    CU(cudaSetDevice(b->device));
+    const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
+    const bool use_xpad = d_xpad && b->P.pad_len;
+    Slot &s = b->slot[0];
+    for (size_t f0 = 0; f0 < n_frames; f0 += b->chunk) {
+        const size_t n_out = std::min(b->chunk, n_frames - f0);
+        const bool next_here = f0 + n_out < n_frames || has_next;
+        const size_t fa = n_out + (next_here ? 1 : 0);
+        const size_t hist = f0 * 1152 + history_samples;
+        Mp2Chunk c = chunk_of(b, s, d_pcm + f0 * 1152 * nch, -(long)hist, use_xpad ? d_xpad + f0 * rec : nullptr,
+                              d_out + f0 * lg, (int)fa, (int)n_out);
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream);
+        CU(cudaGetLastError());
+        s.last_fa = (int)fa;
+        b->last_slot = 0;
+    }
+    return 0;
+}
+
+void *tlb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void tlb_host_free(void *p) { cudaFreeHost(p); }
+
+long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes)
+{
+    if (!b || !dst) return fail(TLB_E_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    Slot &s = b->slot[b->last_slot];
+    CU(cudaStreamSynchronize(s.stream));
+    const size_t fa = (size_t)s.last_fa;
+    const void *src = nullptr;
+    size_t avail = 0;
+    switch (what) {
+    case TLB_TAP_SB_SAMPLE: src = s.sb; avail = fa * (size_t)b->P.nch * 1152 * sizeof(double); break;
+    case TLB_TAP_SCALAR_PRE: src = s.scalar_pre; avail = fa * 192; break;
+    case TLB_TAP_J_SCALE: src = s.j_scale; avail = fa * 96; break;
+    case TLB_TAP_SMR: src = s.smr; avail = fa * 64 * sizeof(double); break;
+    case TLB_TAP_SIDE: src = s.side; avail = fa * sizeof(tlb_side); break;
+    default: return fail(TLB_E_ARG, "unknown tap");
+    }
+    const size_t n = std::min(avail, bytes);
+    CU(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
+    return (long)n;
+}
+
+} // extern "C"

@@ -1,0 +1,34 @@
+// mp2_device.h -- host <-> kernel interface of the MP2 DAB encode path (internal; not the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/toolame_b200.h"
+
+// Per-stream constants handed to every kernel by value.
+struct Mp2Params {
+    int nch, sblimit, tablenum;
+    int mode, mode_ext, jsbound;        // as configured (toolame_set_channel_mode); JS frames re-decide per frame
+    int version, bitrate_index, sfreq_idx;
+    int dab_ext, lg_frame, pad_len;
+    int psy_freq, sub_size, cb_count;   // psy-1 table selectors (psycho_1.c:42-56)
+    int bitrate_per_ch;                 // kbit/s per channel (psycho_1_threshold's ATH offset switch)
+};
+
+// Device buffers of one chunk (frames analysed = n_out + has_next).
+struct Mp2Chunk {
+    const int16_t *pcm;     // interleaved s16; element 0 = first sample of the chunk's first frame
+    long lo;                // lowest readable sample index relative to pcm (<= 0); below it the signal is 0
+    const uint8_t *xpad;    // NULL or records of pad_len+1 bytes, one per analysed frame
+    double *sb;             // [fa][nch][36][32]
+    uint8_t *scalar_pre;    // [fa][2][3][32]
+    uint8_t *j_scale;       // [fa][3][32]
+    double *smr;            // [fa][2][32]
+    tlb_side *side;         // [fa]
+    uint8_t *out;           // [n_out][lg_frame]
+    int fa;                 // frames analysed
+    int n_out;              // frames written
+};
+
+// Launch the four kernels of one chunk on `stream`; returns the number of launches issued.
+int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const uint8_t *d_map, cudaStream_t stream);
