@@ -97,6 +97,16 @@ TLB_API void *tlb_batch_stream(tlb_batch *b);
 /* Number of kernel launches issued by this encoder so far. */
 TLB_API uint64_t tlb_batch_launches(const tlb_batch *b);
 
+/* Per-kernel device time: with profiling enabled every chunk records CUDA events around its kernels on the
+ * launching stream; tlb_batch_kernel_times syncs, returns the summed milliseconds and launch counts of the four
+ * kernels (tlb_kernel_name(0..3)) since the last call, and clears them. */
+TLB_API int tlb_batch_profile(tlb_batch *b, int enable);
+TLB_API int tlb_batch_kernel_times(tlb_batch *b, double ms[4], uint64_t launches[4]);
+TLB_API const char *tlb_kernel_name(int k);
+/* Measured FP64 rate of the device, TFLOP/s with mul+add = 2 flop: DFMA chains, and DMUL+DADD chains (the only
+ * form this path may use: the reference is built without FMA contraction). */
+TLB_API int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops);
+
 /* Pinned host memory for pcm / out buffers. */
 TLB_API void *tlb_host_alloc(size_t bytes);
 TLB_API void tlb_host_free(void *p);

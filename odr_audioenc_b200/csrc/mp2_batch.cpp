@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "mp2_device.h"
 
@@ -122,7 +123,19 @@ struct tlb_batch {
     uint8_t *d_map = nullptr;
     uint64_t launches = 0;
     int last_slot = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events; // 5 per profiled chunk
+    cudaEvent_t *next_events()
+    {
+        if (!profile) return nullptr;
+        const size_t at = prof_events.size();
+        prof_events.resize(at + 5);
+        for (size_t i = at; i < at + 5; i++) cudaEventCreate(&prof_events[i]);
+        return &prof_events[at];
+    }
 };
+
+const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS] = {"k_filterbank", "k_psy1", "k_alloc", "k_pack"};
 
 namespace {
 
@@ -259,7 +272,7 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
                            (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
         if (use_xpad) CU(cudaMemcpyAsync(s.d_xpad, xpad + f0 * rec, fa * rec, cudaMemcpyHostToDevice, s.stream));
         Mp2Chunk c = chunk_of(b, s, s.d_pcm + HALO * nch, -(long)hist, use_xpad ? s.d_xpad : nullptr, s.d_out, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream);
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream, b->next_events());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + f0 * lg, s.d_out, n_out * lg, cudaMemcpyDeviceToHost, s.stream));
         s.last_fa = (int)fa;
@@ -285,11 +298,49 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
         const size_t hist = f0 * 1152 + history_samples;
         Mp2Chunk c = chunk_of(b, s, d_pcm + f0 * 1152 * nch, -(long)hist, use_xpad ? d_xpad + f0 * rec : nullptr,
                               d_out + f0 * lg, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream);
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream, b->next_events());
         CU(cudaGetLastError());
         s.last_fa = (int)fa;
         b->last_slot = 0;
     }
+    return 0;
+}
+
+int tlb_batch_profile(tlb_batch *b, int enable)
+{
+    if (!b) return fail(TLB_E_ARG, "NULL argument");
+    b->profile = enable != 0;
+    return 0;
+}
+
+int tlb_batch_kernel_times(tlb_batch *b, double ms[4], uint64_t launches[4])
+{
+    if (!b || !ms || !launches) return fail(TLB_E_ARG, "NULL argument");
+    int rc = tlb_batch_sync(b);
+    if (rc) return rc;
+    for (int k = 0; k < MP2_N_KERNELS; k++) { ms[k] = 0; launches[k] = 0; }
+    for (size_t at = 0; at + 5 <= b->prof_events.size(); at += 5)
+        for (int k = 0; k < MP2_N_KERNELS; k++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, b->prof_events[at + k], b->prof_events[at + k + 1]) == cudaSuccess) {
+                ms[k] += t;
+                launches[k]++;
+            }
+        }
+    for (auto e : b->prof_events) cudaEventDestroy(e);
+    b->prof_events.clear();
+    return 0;
+}
+
+const char *tlb_kernel_name(int k) { return k >= 0 && k < MP2_N_KERNELS ? MP2_KERNEL_NAMES[k] : ""; }
+
+int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops)
+{
+    if (!dfma_tflops || !dmul_dadd_tflops) return fail(TLB_E_ARG, "NULL argument");
+    CU(cudaSetDevice(device));
+    *dfma_tflops = mp2_fp64_probe(true, nullptr);
+    *dmul_dadd_tflops = mp2_fp64_probe(false, nullptr);
+    if (*dfma_tflops < 0 || *dmul_dadd_tflops < 0) return fail(TLB_E_CUDA, "fp64 probe failed");
     return 0;
 }
 

@@ -31,4 +31,10 @@ struct Mp2Chunk {
 };
 
 // Launch the four kernels of one chunk on `stream`; returns the number of launches issued.
-int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const uint8_t *d_map, cudaStream_t stream);
+// ev: NULL, or 5 events recorded before / between / after the kernels (per-kernel timing).
+int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const uint8_t *d_map, cudaStream_t stream, cudaEvent_t *ev);
+constexpr int MP2_N_KERNELS = 4;
+extern const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS];
+
+// Measured FP64 rate of the device in TFLOP/s (mul+add counted as 2): DFMA chains, or DMUL+DADD chains.
+double mp2_fp64_probe(bool fma, cudaStream_t stream);
