@@ -120,7 +120,7 @@ struct tlb_batch {
     int device = 0;
     size_t chunk = 0;
     Slot slot[2];
-    uint8_t *d_map = nullptr;
+    Mp2PsyTables *d_tables = nullptr;
     uint64_t launches = 0;
     int last_slot = 0;
     bool profile = false;
@@ -206,16 +206,29 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
     b->chunk = max_chunk_frames ? max_chunk_frames : DEFAULT_CHUNK;
     for (int i = 0; i < 2; i++)
         if ((rc = alloc_slot(b, b->slot[i]))) { tlb_batch_destroy(b); return rc; }
-    {   // FFT line -> threshold-table partition (ref: psycho_1.c:160-168); lines above the last partition keep the
+    {
+        Mp2PsyTables T;
+        std::memset(&T, 0, sizeof T);
+        const int fq = P.psy_freq;
+        // FFT line -> threshold-table partition (ref: psycho_1.c:160-168); lines above the last partition keep the
         // allocator's zero (mem.c:21)
-        uint8_t map[512];
-        std::memset(map, 0, sizeof map);
         for (int i = 1; i < P.sub_size; i++)
-            for (int j = MP2_LTG_LINE[P.psy_freq][i - 1]; j <= MP2_LTG_LINE[P.psy_freq][i]; j++) map[j] = (uint8_t)i;
-        if (cudaMalloc(&b->d_map, 512) != cudaSuccess ||
-            cudaMemcpy(b->d_map, map, 512, cudaMemcpyHostToDevice) != cudaSuccess) {
+            for (int j = MP2_LTG_LINE[fq][i - 1]; j <= MP2_LTG_LINE[fq][i]; j++) T.map[j] = (uint8_t)i;
+        std::memset(T.band, 255, sizeof T.band);
+        for (int i = 0; i + 1 < P.cb_count; i++)
+            for (int j = MP2_CBOUND[fq][i]; j < MP2_CBOUND[fq][i + 1]; j++) T.band[j] = (uint8_t)i;
+        // psycho_1_minimum_mask's scan over the partitions is data independent: replay it (ref: psycho_1.c:546-558)
+        int j = 1;
+        for (int i = 0; i < P.sblimit; i++) {
+            if (j >= P.sub_size - 1) { T.mm_j0[i] = 255; T.mm_j1[i] = 255; continue; }
+            T.mm_j0[i] = (uint8_t)j;
+            while (j < P.sub_size && (MP2_LTG_LINE[fq][j] >> 4) == i) j++;
+            T.mm_j1[i] = (uint8_t)j;
+        }
+        if (cudaMalloc(&b->d_tables, sizeof T) != cudaSuccess ||
+            cudaMemcpy(b->d_tables, &T, sizeof T, cudaMemcpyHostToDevice) != cudaSuccess) {
             tlb_batch_destroy(b);
-            return fail(TLB_E_CUDA, "map upload failed");
+            return fail(TLB_E_CUDA, "table upload failed");
         }
     }
     *out = b;
@@ -230,7 +243,7 @@ void tlb_batch_destroy(tlb_batch *b)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
-    cudaFree(b->d_map);
+    cudaFree(b->d_tables);
     delete b;
 }
 
@@ -272,7 +285,7 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
                            (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
         if (use_xpad) CU(cudaMemcpyAsync(s.d_xpad, xpad + f0 * rec, fa * rec, cudaMemcpyHostToDevice, s.stream));
         Mp2Chunk c = chunk_of(b, s, s.d_pcm + HALO * nch, -(long)hist, use_xpad ? s.d_xpad : nullptr, s.d_out, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream, b->next_events());
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, s.stream, b->next_events());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + f0 * lg, s.d_out, n_out * lg, cudaMemcpyDeviceToHost, s.stream));
         s.last_fa = (int)fa;
@@ -298,7 +311,7 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
         const size_t hist = f0 * 1152 + history_samples;
         Mp2Chunk c = chunk_of(b, s, d_pcm + f0 * 1152 * nch, -(long)hist, use_xpad ? d_xpad + f0 * rec : nullptr,
                               d_out + f0 * lg, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_map, s.stream, b->next_events());
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, s.stream, b->next_events());
         CU(cudaGetLastError());
         s.last_fa = (int)fa;
         b->last_slot = 0;

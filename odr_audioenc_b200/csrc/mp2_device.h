@@ -15,6 +15,14 @@ struct Mp2Params {
     int bitrate_per_ch;                 // kbit/s per channel (psycho_1_threshold's ATH offset switch)
 };
 
+// Per-stream lookup tables of the psychoacoustic model, built on the host at create time.
+struct Mp2PsyTables {
+    uint8_t map[512];    // FFT line -> threshold partition (psycho_1.c:160-168); 0 above the last partition
+    uint8_t band[512];   // FFT line -> critical band (critband.h boundaries); 255 outside every band
+    uint8_t mm_j0[32];   // per subband: first threshold partition of psycho_1_minimum_mask's scan (255: past the end)
+    uint8_t mm_j1[32];   // ... and one past its last partition
+};
+
 // Device buffers of one chunk (frames analysed = n_out + has_next).
 struct Mp2Chunk {
     const int16_t *pcm;     // interleaved s16; element 0 = first sample of the chunk's first frame
@@ -32,7 +40,7 @@ struct Mp2Chunk {
 
 // Launch the four kernels of one chunk on `stream`; returns the number of launches issued.
 // ev: NULL, or 5 events recorded before / between / after the kernels (per-kernel timing).
-int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const uint8_t *d_map, cudaStream_t stream, cudaEvent_t *ev);
+int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const Mp2PsyTables *tables, cudaStream_t stream, cudaEvent_t *ev);
 constexpr int MP2_N_KERNELS = 4;
 extern const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS];
 
