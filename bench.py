@@ -34,7 +34,9 @@ UNIT = "audio-s/s"
 ALG_BYTES_PER_FRAME = NCH * 1152 * 2 + 3 * KBPS
 KERNEL_ALG = {  # per frame: (bytes the kernel must move, FP64 flops it must do), stated in DESIGN.md
     "k_filterbank": (NCH * 1152 * 2 + NCH * 1152 * 8 + 192 + 96, NCH * 74844 + 2304),
-    "k_psy1": (NCH * 1024 * 2 + NCH * 32 * 8 + 192, NCH * 27334),
+    "k_spectrum": (NCH * (1024 * 2 + 2 * 512 * 8 + 128 + 256), NCH * 27334),
+    "k_label": (NCH * (2 * 512 * 8 + 128 + 1128), 0),
+    "k_threshold": (NCH * (1128 + 256 + 256) + 192, 0),
     "k_alloc": (192 + NCH * 32 * 8 + 336, 0),
     "k_pack": (NCH * 1152 * 8 + 336 + 96 + 3 * KBPS, NCH * 3888),
 }
@@ -263,8 +265,9 @@ def main():
     launches0 = enc.launches
     dev_s, _ = timed(step_device, args.steps, args.warmup, sync_each=False)
     # per-kernel CUDA-event times of the timed region (+ warm-up steps: same work per step)
-    ms = (C.c_double * 4)()
-    cnt = (C.c_uint64 * 4)()
+    NK = L.tlb_kernel_count()
+    ms = (C.c_double * NK)()
+    cnt = (C.c_uint64 * NK)()
     L.tlb_batch_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.tlb_batch_kernel_times(enc._h, ms, cnt)
     L.tlb_batch_profile(enc._h, 0)
@@ -315,15 +318,14 @@ def main():
     parity_frames_equal = int((got.reshape(chk_n, -1) == want.reshape(chk_n, -1)).all(axis=1).sum())
 
     # ---- roofline of the dominant kernel
-    names = [L.tlb_kernel_name(k) for k in range(4)]
     L.tlb_kernel_name.restype = C.c_char_p
-    names = [L.tlb_kernel_name(k).decode() for k in range(4)]
+    names = [L.tlb_kernel_name(k).decode() for k in range(NK)]
     per_kernel = {}
-    total_ms = sum(ms[k] for k in range(4)) or 1.0
-    for k in range(4):
+    total_ms = sum(ms[k] for k in range(NK)) or 1.0
+    for k in range(NK):
         n_l = max(int(cnt[k]), 1)
         per_kernel[names[k]] = {"launches": int(cnt[k]), "avg_ms": ms[k] / n_l, "share": ms[k] / total_ms}
-    top = max(range(4), key=lambda k: ms[k])
+    top = max(range(NK), key=lambda k: ms[k])
     frames_per_launch = n_frames * (args.steps + args.warmup) / max(int(cnt[top]), 1)
     peaks = {}
     try:

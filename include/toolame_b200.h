@@ -98,10 +98,12 @@ TLB_API void *tlb_batch_stream(tlb_batch *b);
 TLB_API uint64_t tlb_batch_launches(const tlb_batch *b);
 
 /* Per-kernel device time: with profiling enabled every chunk records CUDA events around its kernels on the
- * launching stream; tlb_batch_kernel_times syncs, returns the summed milliseconds and launch counts of the four
- * kernels (tlb_kernel_name(0..3)) since the last call, and clears them. */
+ * launching stream; tlb_batch_kernel_times syncs, returns the summed milliseconds and launch counts of the
+ * tlb_kernel_count() kernels (names: tlb_kernel_name(k)) since the last call, and clears them.  ms and launches
+ * point at tlb_kernel_count() elements each. */
 TLB_API int tlb_batch_profile(tlb_batch *b, int enable);
-TLB_API int tlb_batch_kernel_times(tlb_batch *b, double ms[4], uint64_t launches[4]);
+TLB_API int tlb_batch_kernel_times(tlb_batch *b, double *ms, uint64_t *launches);
+TLB_API int tlb_kernel_count(void);
 TLB_API const char *tlb_kernel_name(int k);
 /* Measured FP64 rate of the device, TFLOP/s with mul+add = 2 flop: DFMA chains, and DMUL+DADD chains (the only
  * form this path may use: the reference is built without FMA contraction). */

@@ -37,7 +37,9 @@ int fail(int code, const std::string &msg)
 
 constexpr int HALO = 512;         // samples of history staged per chunk (the filterbank needs 480, psy-1 192)
 constexpr int HALO_NEEDED = 480;
-constexpr size_t DEFAULT_CHUNK = 148 * 128; // frames per launch: a multiple of the SM count
+constexpr size_t DEFAULT_CHUNK = 148 * 512; // frames per launch: a multiple of the SM count, large enough to fill the
+                                            // thread-per-frame kernels (k_label, k_alloc) with warps
+constexpr size_t HOST_CHUNK = 148 * 256;    // host-buffer path: smaller pieces so copies overlap the kernels
 
 int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
 {
@@ -104,7 +106,9 @@ struct Slot {
     uint8_t *d_out = nullptr;
     double *sb = nullptr;
     uint8_t *scalar_pre = nullptr, *j_scale = nullptr;
-    double *smr = nullptr;
+    double *smr = nullptr, *psy_x = nullptr, *psy_w = nullptr, *spike = nullptr;
+    unsigned *psy_cand = nullptr, *psy_t0 = nullptr;
+    Mp2Maskers *maskers = nullptr;
     tlb_side *side = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -124,18 +128,18 @@ struct tlb_batch {
     uint64_t launches = 0;
     int last_slot = 0;
     bool profile = false;
-    std::vector<cudaEvent_t> prof_events; // 5 per profiled chunk
+    std::vector<cudaEvent_t> prof_events; // MP2_N_KERNELS + 1 per profiled chunk
     cudaEvent_t *next_events()
     {
         if (!profile) return nullptr;
         const size_t at = prof_events.size();
-        prof_events.resize(at + 5);
-        for (size_t i = at; i < at + 5; i++) cudaEventCreate(&prof_events[i]);
+        prof_events.resize(at + MP2_N_KERNELS + 1);
+        for (size_t i = at; i < at + MP2_N_KERNELS + 1; i++) cudaEventCreate(&prof_events[i]);
         return &prof_events[at];
     }
 };
 
-const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS] = {"k_filterbank", "k_psy1", "k_alloc", "k_pack"};
+const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS] = {"k_filterbank", "k_spectrum", "k_label", "k_threshold", "k_alloc", "k_pack"};
 
 namespace {
 
@@ -149,6 +153,13 @@ int alloc_slot(tlb_batch *b, Slot &s)
     CU(cudaMalloc(&s.scalar_pre, fa * 192));
     CU(cudaMalloc(&s.j_scale, fa * 96));
     CU(cudaMalloc(&s.smr, fa * 64 * sizeof(double)));
+    const size_t items = fa * nch, tiles = (items + 31) / 32;
+    CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
+    CU(cudaMalloc(&s.psy_w, tiles * 512 * 32 * sizeof(double)));
+    CU(cudaMalloc(&s.psy_cand, items * 16 * sizeof(unsigned)));
+    CU(cudaMalloc(&s.psy_t0, items * 16 * sizeof(unsigned)));
+    CU(cudaMalloc(&s.spike, items * 32 * sizeof(double)));
+    CU(cudaMalloc(&s.maskers, items * sizeof(Mp2Maskers)));
     CU(cudaMalloc(&s.side, fa * sizeof(tlb_side)));
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -159,6 +170,7 @@ void free_slot(Slot &s)
 {
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
+    cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s = Slot();
@@ -170,7 +182,8 @@ Mp2Chunk chunk_of(const tlb_batch *b, const Slot &s, const int16_t *pcm, long lo
     (void)b;
     Mp2Chunk c;
     c.pcm = pcm; c.lo = lo; c.xpad = xpad; c.sb = s.sb; c.scalar_pre = s.scalar_pre; c.j_scale = s.j_scale;
-    c.smr = s.smr; c.side = s.side; c.out = out; c.fa = fa; c.n_out = n_out;
+    c.smr = s.smr; c.side = s.side; c.psy_x = s.psy_x; c.psy_w = s.psy_w; c.psy_cand = s.psy_cand; c.psy_t0 = s.psy_t0;
+    c.spike = s.spike; c.maskers = s.maskers; c.out = out; c.fa = fa; c.n_out = n_out;
     return c;
 }
 
@@ -274,9 +287,10 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
     const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
     const bool use_xpad = xpad && b->P.pad_len;
     size_t k = 0;
-    for (size_t f0 = 0; f0 < n_frames; f0 += b->chunk, k++) {
+    const size_t chunk = std::min(b->chunk, HOST_CHUNK);
+    for (size_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
         Slot &s = b->slot[k & 1];
-        const size_t n_out = std::min(b->chunk, n_frames - f0);
+        const size_t n_out = std::min(chunk, n_frames - f0);
         const bool next_here = f0 + n_out < n_frames || has_next;
         const size_t fa = n_out + (next_here ? 1 : 0);
         const size_t hist = std::min<size_t>(HALO, f0 * 1152 + history_samples);
@@ -326,13 +340,13 @@ int tlb_batch_profile(tlb_batch *b, int enable)
     return 0;
 }
 
-int tlb_batch_kernel_times(tlb_batch *b, double ms[4], uint64_t launches[4])
+int tlb_batch_kernel_times(tlb_batch *b, double *ms, uint64_t *launches)
 {
     if (!b || !ms || !launches) return fail(TLB_E_ARG, "NULL argument");
     int rc = tlb_batch_sync(b);
     if (rc) return rc;
     for (int k = 0; k < MP2_N_KERNELS; k++) { ms[k] = 0; launches[k] = 0; }
-    for (size_t at = 0; at + 5 <= b->prof_events.size(); at += 5)
+    for (size_t at = 0; at + MP2_N_KERNELS + 1 <= b->prof_events.size(); at += MP2_N_KERNELS + 1)
         for (int k = 0; k < MP2_N_KERNELS; k++) {
             float t = 0;
             if (cudaEventElapsedTime(&t, b->prof_events[at + k], b->prof_events[at + k + 1]) == cudaSuccess) {
@@ -344,6 +358,8 @@ int tlb_batch_kernel_times(tlb_batch *b, double ms[4], uint64_t launches[4])
     b->prof_events.clear();
     return 0;
 }
+
+int tlb_kernel_count(void) { return MP2_N_KERNELS; }
 
 const char *tlb_kernel_name(int k) { return k >= 0 && k < MP2_N_KERNELS ? MP2_KERNEL_NAMES[k] : ""; }
 

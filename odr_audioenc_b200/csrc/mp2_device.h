@@ -23,6 +23,15 @@ struct Mp2PsyTables {
     uint8_t mm_j1[32];   // ... and one past its last partition
 };
 
+// Surviving maskers of one (frame, channel), in the order psycho_1_threshold visits them.
+struct Mp2Maskers {
+    double t_x[96];       // tonal: level in dB
+    double n_x[28];       // noise
+    uint8_t t_part[96];   // threshold-table partition of the masker's line (index into the bark table)
+    uint8_t n_part[28];
+    int n_tone, n_noise;
+};
+
 // Device buffers of one chunk (frames analysed = n_out + has_next).
 struct Mp2Chunk {
     const int16_t *pcm;     // interleaved s16; element 0 = first sample of the chunk's first frame
@@ -31,6 +40,12 @@ struct Mp2Chunk {
     double *sb;             // [fa][nch][36][32]
     uint8_t *scalar_pre;    // [fa][2][3][32]
     uint8_t *j_scale;       // [fa][3][32]
+    double *psy_x;          // [ceil(fa*nch/32)][512][32]  dB spectrum, tile layout (see mp2_kernels.cu)
+    double *psy_w;          // same layout: noise-centre weight of each line
+    unsigned *psy_cand;     // [fa*nch][16] tonal-candidate mask
+    unsigned *psy_t0;       // [fa*nch][16] candidates passing the neighbourhood test on the unmodified spectrum
+    double *spike;          // [fa*nch][32]
+    Mp2Maskers *maskers;    // [fa*nch]
     double *smr;            // [fa][2][32]
     tlb_side *side;         // [fa]
     uint8_t *out;           // [n_out][lg_frame]
@@ -38,10 +53,10 @@ struct Mp2Chunk {
     int n_out;              // frames written
 };
 
-// Launch the four kernels of one chunk on `stream`; returns the number of launches issued.
-// ev: NULL, or 5 events recorded before / between / after the kernels (per-kernel timing).
+// Launch the kernels of one chunk on `stream`; returns the number of launches issued.
+// ev: NULL, or MP2_N_KERNELS+1 events recorded before / between / after the kernels (per-kernel timing).
 int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const Mp2PsyTables *tables, cudaStream_t stream, cudaEvent_t *ev);
-constexpr int MP2_N_KERNELS = 4;
+constexpr int MP2_N_KERNELS = 6;
 extern const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS];
 
 // Measured FP64 rate of the device in TFLOP/s (mul+add counted as 2): DFMA chains, or DMUL+DADD chains.
