@@ -317,8 +317,18 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
     CU(cudaSetDevice(b->device));
     const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
     const bool use_xpad = d_xpad && b->P.pad_len;
-    Slot &s = b->slot[0];
-    for (size_t f0 = 0; f0 < n_frames; f0 += b->chunk) {
+    // Chunks alternate between the two slots and their streams so that kernels of neighbouring chunks overlap on
+    // the GPU (several kernels are latency-bound on their own).  Towards the caller the call behaves as if it ran
+    // on slot 0's stream: slot 1's stream forks from it here and joins it at the end.
+    const size_t n_chunks = (n_frames + b->chunk - 1) / b->chunk;
+    const bool two = n_chunks > 1 && !b->profile; // per-kernel event timing wants the kernels one at a time
+    if (two) {
+        CU(cudaEventRecord(b->slot[0].done, b->slot[0].stream));
+        CU(cudaStreamWaitEvent(b->slot[1].stream, b->slot[0].done, 0));
+    }
+    size_t k = 0;
+    for (size_t f0 = 0; f0 < n_frames; f0 += b->chunk, k++) {
+        Slot &s = b->slot[two ? (k & 1) : 0];
         const size_t n_out = std::min(b->chunk, n_frames - f0);
         const bool next_here = f0 + n_out < n_frames || has_next;
         const size_t fa = n_out + (next_here ? 1 : 0);
@@ -328,7 +338,11 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
         b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, s.stream, b->next_events());
         CU(cudaGetLastError());
         s.last_fa = (int)fa;
-        b->last_slot = 0;
+        b->last_slot = two ? (int)(k & 1) : 0;
+    }
+    if (two) {
+        CU(cudaEventRecord(b->slot[1].done, b->slot[1].stream));
+        CU(cudaStreamWaitEvent(b->slot[0].stream, b->slot[1].done, 0));
     }
     return 0;
 }
