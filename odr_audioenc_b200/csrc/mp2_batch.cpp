@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -287,7 +288,11 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
     const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
     const bool use_xpad = xpad && b->P.pad_len;
     size_t k = 0;
-    const size_t chunk = std::min(b->chunk, HOST_CHUNK);
+    size_t chunk = std::min(b->chunk, HOST_CHUNK);
+    if (const char *e = std::getenv("TLB_HOST_CHUNK")) { // tuning knob: frames per host<->device pipeline stage
+        const long v = std::atol(e);
+        if (v > 0) chunk = std::min(b->chunk, (size_t)v);
+    }
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
         Slot &s = b->slot[k & 1];
         const size_t n_out = std::min(chunk, n_frames - f0);
