@@ -151,9 +151,10 @@ int alloc_slot(tlb_batch *b, Slot &s)
     CU(cudaMalloc(&s.d_xpad, fa * (size_t)(b->P.pad_len + 1)));
     CU(cudaMalloc(&s.d_out, b->chunk * (size_t)b->P.lg_frame));
     CU(cudaMalloc(&s.sb, fa * nch * 1152 * sizeof(double)));
-    CU(cudaMalloc(&s.scalar_pre, fa * 192));
+    const size_t fa32 = (fa + 31) / 32 * 32; // frame-tile layouts are padded to whole tiles of 32 frames
+    CU(cudaMalloc(&s.scalar_pre, fa32 * 192));
     CU(cudaMalloc(&s.j_scale, fa * 96));
-    CU(cudaMalloc(&s.smr, fa * 64 * sizeof(double)));
+    CU(cudaMalloc(&s.smr, fa32 * 64 * sizeof(double)));
     const size_t items = fa * nch, tiles = (items + 31) / 32;
     CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
     CU(cudaMalloc(&s.psy_w, tiles * 512 * 32 * sizeof(double)));
@@ -419,6 +420,18 @@ long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes)
     default: return fail(TLB_E_ARG, "unknown tap");
     }
     const size_t n = std::min(avail, bytes);
+    if (what == TLB_TAP_SCALAR_PRE || what == TLB_TAP_SMR) {
+        // stored on the device in the frame-tile layout [frame/32][field][frame%32]: put frames back in order
+        const size_t nf = what == TLB_TAP_SMR ? 64 : 192, esz = what == TLB_TAP_SMR ? sizeof(double) : 1;
+        const size_t fa32 = (fa + 31) / 32 * 32;
+        std::vector<unsigned char> raw(fa32 * nf * esz), lin(fa * nf * esz);
+        CU(cudaMemcpy(raw.data(), src, raw.size(), cudaMemcpyDeviceToHost));
+        for (size_t f = 0; f < fa; f++)
+            for (size_t k = 0; k < nf; k++)
+                std::memcpy(&lin[(f * nf + k) * esz], &raw[(((f >> 5) * nf + k) * 32 + (f & 31)) * esz], esz);
+        std::memcpy(dst, lin.data(), n);
+        return (long)n;
+    }
     CU(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
     return (long)n;
 }
