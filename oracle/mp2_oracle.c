@@ -14,6 +14,8 @@
 
 #include "mp2_tables.h"
 #include "mp2_alloc_tables.h"
+#include "mp2_psy2_tables.h"
+#include "mp2_psy2_init.h"
 
 #define DBMIN (-200.0)      /* ref: encoder.h:31 */
 #define POWERNORM 90.3090   /* ref: encoder.h:34 */
@@ -445,6 +447,119 @@ void mp2o_psy1_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame,
     for (int i = c->sblimit; i < 32; i++) smr[i] = 0, ltmin[i] = 0;
 }
 
+/* ------------------------------------------------------------------ psychoacoustic model 2 */
+
+typedef struct { double energy[513], phi[513]; } p2_spec;
+
+/* ref: psycho_2.c:80-92 (window of block B = raw samples [576B-480, 576B+544), zeros before the stream start)
+ * and fft.c:1230-1275 (psycho_2_fft, built without NEWATAN) */
+static void psy2_spectrum(const int16_t *pcm, int nch, int ch, long block, p2_spec *S)
+{
+    const double PI = 3.14159265358979; /* ref: common.h:26 */
+    double w[1024];
+    for (int j = 0; j < 1024; j++) {
+        long idx = 576 * block - 480 + j;
+        w[j] = MP2_P2_WINDOW[j] * (idx < 0 ? 0.0 : (double)pcm[idx * nch + ch]);
+    }
+    mp2o_fht1024(w);
+    S->energy[0] = w[0] * w[0];
+    S->phi[0] = 0; /* never written by the reference: stays the allocator's zero */
+    for (int i = 1, j = 1023; i < 512; i++, j--) {
+        double a = w[i], b = w[j];
+        S->energy[i] = (a * a + b * b) / 2.0;
+        if (S->energy[i] < 0.0005) {
+            S->energy[i] = 0.0005;
+            S->phi[i] = 0;
+        } else S->phi[i] = atan2(-(double)a, (double)b) + PI / 4;
+    }
+    S->energy[512] = w[512] * w[512];
+    S->phi[512] = atan2(0.0, (double)w[512]);
+}
+
+/* ref: psycho_2.c:52-254 for one channel of one frame, stateless: the unpredictability measure of block B needs
+ * r = sqrt(energy) and phi of blocks B-1 and B-2, which are zeros (not the FFT of silence) before the stream start
+ * (psycho_2.c:322-326). */
+void mp2o_psy2_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame, double smr[32])
+{
+    static mp2_psy2_tables T;
+    static double T_for = 0;
+    static p2_spec S[3];
+    const double nmt = 5.5, LN_TO_LOG10 = 0.2302585093;
+    double sfreq = (double)c->fs_hz; /* (FLOAT) s_freq[version][idx] * 1000 */
+    if (T_for != sfreq) { mp2_psy2_init(&T, sfreq); T_for = sfreq; }
+    const double *absthr = MP2_ABSTHR[T.absthr_table];
+    double snrtmp[2][32];
+    for (int i = 0; i < 2; i++) {
+        long B = 2 * frame + i;
+        double cm[513], grouped_e[64], grouped_c[64], ecb[64], cb[64], bc[64], nb[64], fthr[513];
+        psy2_spectrum(pcm, c->nch, ch, B, &S[0]);
+        for (int a = 1; a <= 2; a++)
+            if (B - a >= 0) psy2_spectrum(pcm, c->nch, ch, B - a, &S[a]);
+        for (int j = 0; j < 513; j++) {
+            double r1 = B - 1 >= 0 ? sqrt(S[1].energy[j]) : 0, p1 = B - 1 >= 0 ? S[1].phi[j] : 0;
+            double r2 = B - 2 >= 0 ? sqrt(S[2].energy[j]) : 0, p2 = B - 2 >= 0 ? S[2].phi[j] : 0;
+            double r_prime = 2.0 * r1 - r2, phi_prime = 2.0 * p1 - p2;
+            double rn = sqrt(S[0].energy[j]), phi = S[0].phi[j];
+            double temp1 = rn * cos(phi) - r_prime * cos(phi_prime);
+            double temp2 = rn * sin(phi) - r_prime * sin(phi_prime);
+            double temp3 = rn + fabs(r_prime);
+            cm[j] = temp3 != 0 ? sqrt(temp1 * temp1 + temp2 * temp2) / temp3 : 0;
+        }
+        const double *energy = S[0].energy;
+        for (int j = 1; j < 64; j++) grouped_e[j] = grouped_c[j] = 0;
+        grouped_e[0] = energy[0];
+        grouped_c[0] = energy[0] * cm[0];
+        for (int j = 1; j < 513; j++) {
+            grouped_e[T.partition[j]] += energy[j];
+            grouped_c[T.partition[j]] += energy[j] * cm[j];
+        }
+        for (int j = 0; j < 64; j++) { /* ref: psycho_2.c:163-177 */
+            ecb[j] = 0;
+            cb[j] = 0;
+            for (int k = 0; k < 64; k++)
+                if (T.s[j][k] != 0.0) {
+                    ecb[j] += T.s[j][k] * grouped_e[k];
+                    cb[j] += T.s[j][k] * grouped_c[k];
+                }
+            if (ecb[j] != 0) cb[j] = cb[j] / ecb[j];
+            else cb[j] = 0;
+        }
+        for (int j = 0; j < 64; j++) { /* ref: psycho_2.c:183-198 */
+            if (cb[j] < .05) cb[j] = 0.05;
+            else if (cb[j] > .5) cb[j] = 0.5;
+            double tb = -0.434294482 * log((double)cb[j]) - 0.301029996;
+            bc[j] = T.tmn[j] * tb + nmt * (1.0 - tb);
+            bc[j] = (bc[j] > T.bmax_of[j]) ? bc[j] : T.bmax_of[j];
+            bc[j] = exp((double)-bc[j] * LN_TO_LOG10);
+        }
+        for (int j = 0; j < 64; j++) /* ref: psycho_2.c:205-209 */
+            nb[j] = (T.rnorm[j] && T.numlines[j]) ? ecb[j] * bc[j] / (T.rnorm[j] * T.numlines[j]) : 0;
+        for (int j = 0; j < 513; j++) {
+            double t = nb[T.partition[j]];
+            fthr[j] = (t > absthr[j]) ? t : absthr[j];
+        }
+        for (int j = 0; j < 193; j += 16) { /* ref: psycho_2.c:231-241 */
+            double minthres = 60802371420160.0, sum_energy = 0.0;
+            for (int k = 0; k < 17; k++) {
+                if (minthres > fthr[j + k]) minthres = fthr[j + k];
+                sum_energy += energy[j + k];
+            }
+            snrtmp[i][j / 16] = sum_energy / (minthres * 17.0);
+            snrtmp[i][j / 16] = 4.342944819 * log((double)snrtmp[i][j / 16]);
+        }
+        for (int j = 208; j < 512; j += 16) { /* ref: psycho_2.c:242-251 */
+            double minthres = 0.0, sum_energy = 0.0;
+            for (int k = 0; k < 17; k++) {
+                minthres += fthr[j + k];
+                sum_energy += energy[j + k];
+            }
+            snrtmp[i][j / 16] = sum_energy / minthres;
+            snrtmp[i][j / 16] = 4.342944819 * log((double)snrtmp[i][j / 16]);
+        }
+    }
+    for (int i = 0; i < 32; i++) smr[i] = (snrtmp[0][i] > snrtmp[1][i]) ? snrtmp[0][i] : snrtmp[1][i];
+}
+
 /* ------------------------------------------------------------------ scalefactor select information */
 
 /* ref: encode_new.c:288-354; rewrites sf[] in place */
@@ -623,9 +738,11 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
                 jsamp[b][sb] = sb < sblimit ? .5 * (t->sb_sample[0][b][sb] + t->sb_sample[1][b][sb]) : 0.0;
         scalefactors(jsamp, sblimit, t->j_scale);
     }
-    /* ref: toolame.c:361-452 (psy model switch); only model 1 is restated so far */
-    for (int ch = 0; ch < nch; ch++)
-        mp2o_psy1_frame(c, pcm, ch, n, t->scalar_pre[ch], t->smr[ch], t->ltmin[ch], t->spike[ch]);
+    /* ref: toolame.c:361-452 (psy model switch); models 1 and 2 are restated */
+    for (int ch = 0; ch < nch; ch++) {
+        if (c->psy == 2) mp2o_psy2_frame(c, pcm, ch, n, t->smr[ch]);
+        else mp2o_psy1_frame(c, pcm, ch, n, t->scalar_pre[ch], t->smr[ch], t->ltmin[ch], t->spike[ch]);
+    }
 
     memcpy(t->scalar, t->scalar_pre, sizeof t->scalar);
     for (int ch = 0; ch < nch; ch++) scfsi_pattern(t->scalar[ch], sblimit, t->scfsi[ch]);
@@ -738,7 +855,7 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
 int mp2o_encode(const mp2o_cfg *c, const int16_t *pcm, long n_frames_total, long f0, long f1,
                 const uint8_t *xpad, uint8_t *out, mp2o_tap *taps)
 {
-    if (c->psy != 1) return -1;
+    if (c->psy != 1 && c->psy != 2) return -1;
     static frame_out fo;
     for (long n = f0; n < f1 + 1 && n < n_frames_total; n++) {
         const uint8_t *rec = xpad ? xpad + (size_t)n * (c->pad_len + 1) : NULL;

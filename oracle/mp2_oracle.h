@@ -62,6 +62,7 @@ int mp2o_encode(const mp2o_cfg *c, const int16_t *pcm, long n_frames_total, long
                 const uint8_t *xpad, uint8_t *out, mp2o_tap *taps);
 
 /* stage entry points used by the stage-level tests */
+void mp2o_psy2_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame, double smr[32]);
 void mp2o_filterbank_frame(const int16_t *pcm, int nch, int ch, long frame, double sb[36][32]);
 void mp2o_fht1024(double *x);
 void mp2o_psy1_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame,

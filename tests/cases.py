@@ -15,6 +15,10 @@ SIGNALS = ["S1", "S2", "S3", "S4", "S5", "S6", "S7", "S8"]
 GOLDEN = [(c, s, 10) for c in ("A", "Bs", "Bj", "C", "M48", "T2", "T2j", "D", "E1", "L2") for s in ("S1", "S2", "S8")] + \
          [("Bj", s, 10) for s in ("S3", "S4", "S5", "S6", "S7")] + [("Bj", "PAD", 10), ("C", "PAD", 10), ("T2", "PAD", 10)]
 
+# psychoacoustic model 2 (BASELINE config 5: 48 kHz 256 kbit/s joint stereo) -> tests/golden/psy2_*.npz
+GOLDEN_PSY2 = [("E1", "S1", 10), ("E1", "S8", 10), ("E1", "S2", 10), ("Bj", "S8", 10), ("C", "S1", 10), ("T2j", "S8", 10),
+               ("M48", "S6", 10), ("E1", "S7", 10)]
+
 PAD_LEN = 23
 
 

@@ -11,11 +11,14 @@ import oracle
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("cfg,sig,n", cases.GOLDEN, ids=["%s-%s" % (c, s) for c, s, _ in cases.GOLDEN])
-def test_oracle_matches_golden(cfg, sig, n):
-    g = np.load(os.path.join(GOLD, "%s_%s.npz" % (cfg, sig)))
+ALL_GOLDEN = [(1,) + g for g in cases.GOLDEN] + [(2,) + g for g in cases.GOLDEN_PSY2]
+
+
+@pytest.mark.parametrize("psy,cfg,sig,n", ALL_GOLDEN, ids=["psy%d-%s-%s" % (p, c, s) for p, c, s, _ in ALL_GOLDEN])
+def test_oracle_matches_golden(psy, cfg, sig, n):
+    g = np.load(os.path.join(GOLD, ("%s_%s.npz" if psy == 1 else "psy2_%s_%s.npz") % (cfg, sig)))
     fs, mode, br, pcm, pad_len, xpad = cases.make_case(cfg, sig, n)
-    c = oracle.configure(fs, mode, br, 1, pad_len)
+    c = oracle.configure(fs, mode, br, psy, pad_len)
     out, tap = oracle.encode(c, pcm, xpad=xpad, taps=True)
     assert out.size == n * c.lg_frame == g["bytes"].size
     assert np.array_equal(out, g["bytes"])

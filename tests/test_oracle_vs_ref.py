@@ -33,3 +33,19 @@ def test_oracle_xpad_equal_reference(cfg):
     out, _ = oracle.encode(c, pcm, xpad=xpad)
     ref = reftool.run_ref(pcm, fs, mode, br, 1, pad_len, xpad=xpad)["bytes"]
     assert np.array_equal(out, ref)
+
+
+PSY2_CASES = [("E1", "S1"), ("E1", "S8"), ("E1", "S4"), ("Bs", "S2"), ("C", "S8"), ("A", "S6"), ("M48", "S5"), ("T2j", "S8"),
+              ("L2", "S1"), ("D", "S7")]
+
+
+@pytest.mark.parametrize("cfg,sig", PSY2_CASES, ids=["%s-%s" % cs for cs in PSY2_CASES])
+def test_oracle_psy2_equals_reference(cfg, sig):
+    """psychoacoustic model 2 (inter-frame r/phi state restated as a two-block halo): bytes and SMR bit-identical"""
+    n = 80
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    c = oracle.configure(fs, mode, br, 2)
+    out, tap = oracle.encode(c, pcm, taps=True)
+    r = reftool.run_ref(pcm, fs, mode, br, 2, taps=True)
+    assert np.array_equal(out, r["bytes"])
+    assert np.array_equal(tap["smr"][:, :c.nch], r["tap"]["smr"][:, :c.nch])

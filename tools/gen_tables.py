@@ -165,6 +165,26 @@ def main():
         emit_array(f, "double", "MP2_LTG_HEAR", [7, 134], [v for r in fr_hear for v in r], per_line=8)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
+    # ---- psychoacoustic model 2: Hann window (psycho_2.c:318-319) and absolute threshold tables (absthr.h through
+    # psycho_2_read_absthr, psycho_2.c:422-438)
+    out2 = os.path.join(os.path.dirname(OUT), "mp2_psy2_tables.h")
+    window2 = [0.5 * (1 - math.cos(2.0 * PI_REF * (i - 0.5) / 1024)) for i in range(1024)]
+    lib.psycho_2_read_absthr.argtypes = [C.POINTER(C.c_double), C.c_int]
+    absthr = []
+    for table in range(3):
+        buf = (C.c_double * 513)()
+        lib.psycho_2_read_absthr(buf, table)
+        absthr += list(buf)
+    with open(out2, "w") as f:
+        f.write("// mp2_psy2_tables.h -- GENERATED by tools/gen_tables.py; do not edit.\n"
+                "// Constant tables of psychoacoustic model 2, bit-identical to the reference's values.\n"
+                "#pragma once\n#ifndef MP2_TABLE_QUAL\n#define MP2_TABLE_QUAL static const\n#endif\n\n")
+        f.write("// psy-2 Hann window 0.5*(1-cos(2*PI*(i-0.5)/1024)) with the reference's truncated PI (psycho_2.c:318-319)\n")
+        emit_array(f, "double", "MP2_P2_WINDOW", [1024], window2, per_line=4)
+        f.write("// absolute threshold per FFT line for 32/16, 44.1/22.05 and 48/24 kHz (absthr.h)\n")
+        emit_array(f, "double", "MP2_ABSTHR", [3, 513], absthr, per_line=6)
+    print("wrote", out2, os.path.getsize(out2), "bytes")
+
 
 if __name__ == "__main__":
     main()
