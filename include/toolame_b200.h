@@ -38,7 +38,7 @@ extern "C" {
 #define TLB_E_PARAM   (-1)  /* illegal sample rate / mode / bitrate / psy model / pad length */
 #define TLB_E_CUDA    (-2)  /* CUDA runtime error (tlb_last_error() has the text) */
 #define TLB_E_ARG     (-3)  /* NULL pointer, bad sizes, bad history */
-#define TLB_E_UNSUPP  (-4)  /* legal for the reference, not (yet) built here (psy models 0, 2, 3; 44.1/22.05 kHz padding) */
+#define TLB_E_UNSUPP  (-4)  /* legal for the reference, not (yet) built here (psy models 0, 3; 44.1/22.05 kHz padding) */
 
 /* Stream parameters: what the reference takes through toolame_set_samplerate / _set_channel_mode /
  * _set_bitrate / _set_psy_model / _set_pad (toolame.c:168-262). */
@@ -46,7 +46,7 @@ typedef struct {
     int32_t sample_rate;   /* Hz: 48000, 24000 (DAB); 32000 / 16000 also accepted */
     int32_t channel_mode;  /* 's', 'd', 'j' or 'm' */
     int32_t bitrate;       /* kbit/s, 0 = default of the reference (toolame.c:217-218) */
-    int32_t psy_model;     /* 1 (the odr-audioenc default) */
+    int32_t psy_model;     /* 1 (the odr-audioenc default) or 2 */
     int32_t pad_len;       /* X-PAD + F-PAD bytes reserved per record, 0 = none (toolame_set_pad) */
 } tlb_config;
 
@@ -54,7 +54,7 @@ typedef struct {
 typedef struct {
     int32_t nch, lg_frame, sblimit, tablenum, dab_ext, version, bitrate_index, sfreq_idx;
     int32_t samples_per_frame;  /* 1152 */
-    int32_t halo_samples;       /* PCM history a frame needs before its first sample (480) */
+    int32_t halo_samples;       /* PCM history a frame needs before its first sample (480; 1632 with psy model 2) */
 } tlb_info;
 
 typedef struct tlb_batch tlb_batch;
@@ -73,6 +73,7 @@ TLB_API const char *tlb_last_error(void);
  *                     frame to encode
  *   history_samples   samples per channel that are valid BEFORE pcm (pcm[-history_samples*nch ..]);
  *                     0 = stream start (the reference's zero history), otherwise >= halo_samples
+ *                     (tlb_info: 480, or 1632 with psy model 2)
  *   has_next          1: pcm holds n_frames+1 frames and frame n_frames only lends its ScF-CRC to
  *                        the last emitted frame (a time chunk in the middle of a stream);
  *                     0: stream end, the last frame keeps its own ScF-CRC
@@ -104,7 +105,8 @@ TLB_API uint64_t tlb_batch_launches(const tlb_batch *b);
 TLB_API int tlb_batch_profile(tlb_batch *b, int enable);
 TLB_API int tlb_batch_kernel_times(tlb_batch *b, double *ms, uint64_t *launches);
 TLB_API int tlb_kernel_count(void);
-TLB_API const char *tlb_kernel_name(int k);
+TLB_API const char *tlb_kernel_name(int k);                          /* psy model 1 kernel set */
+TLB_API const char *tlb_batch_kernel_name(const tlb_batch *b, int k); /* this encoder's kernel set ("" = unused slot) */
 /* Measured FP64 rate of the device, TFLOP/s with mul+add = 2 flop: DFMA chains, and DMUL+DADD chains (the only
  * form this path may use: the reference is built without FMA contraction). */
 TLB_API int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops);

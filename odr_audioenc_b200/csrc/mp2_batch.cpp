@@ -18,6 +18,7 @@
 #define MP2_TABLE_QUAL [[maybe_unused]] static const
 #include "mp2_alloc_tables.h"
 #include "mp2_tables.h"
+#include "mp2_psy2_init.h"
 
 namespace {
 
@@ -36,8 +37,9 @@ int fail(int code, const std::string &msg)
             return fail(TLB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                      \
     } while (0)
 
-constexpr int HALO = 512;         // samples of history staged per chunk (the filterbank needs 480, psy-1 192)
-constexpr int HALO_NEEDED = 480;
+constexpr int HALO = 1664;        // samples of history staged per chunk: the filterbank needs 480, psy-1 192, psy-2
+                                  // 1632 (FFT window of the block two before the frame's first: psycho_2.c:80-92)
+constexpr int HALO_PSY1 = 480, HALO_PSY2 = 1632;
 constexpr size_t DEFAULT_CHUNK = 148 * 512; // frames per launch: a multiple of the SM count, large enough to fill the
                                             // thread-per-frame kernels (k_label, k_alloc) with warps
 constexpr size_t HOST_CHUNK = 148 * 256;    // host-buffer path: smaller pieces so copies overlap the kernels
@@ -55,7 +57,8 @@ int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
     default: return fail(TLB_E_PARAM, "illegal sample rate");
     }
     if (c.psy_model < 0 || c.psy_model > 3) return fail(TLB_E_PARAM, "illegal psy model"); // ref: toolame.c:204
-    if (c.psy_model != 1) return fail(TLB_E_UNSUPP, "only psychoacoustic model 1 is built");
+    if (c.psy_model != 1 && c.psy_model != 2) return fail(TLB_E_UNSUPP, "psychoacoustic models 1 and 2 are built");
+    P.psy = c.psy_model;
     switch (c.channel_mode) { // ref: toolame.c:174-200
     case 's': P.mode = 0; P.mode_ext = 0; break;
     case 'j': P.mode = 1; P.mode_ext = 2; break;
@@ -97,7 +100,7 @@ int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
     P.bitrate_per_ch = per_ch;
     I.nch = P.nch; I.lg_frame = P.lg_frame; I.sblimit = P.sblimit; I.tablenum = P.tablenum; I.dab_ext = P.dab_ext;
     I.version = P.version; I.bitrate_index = P.bitrate_index; I.sfreq_idx = P.sfreq_idx;
-    I.samples_per_frame = 1152; I.halo_samples = HALO_NEEDED;
+    I.samples_per_frame = 1152; I.halo_samples = P.psy == 2 ? HALO_PSY2 : HALO_PSY1;
     return 0;
 }
 
@@ -110,6 +113,7 @@ struct Slot {
     double *smr = nullptr, *psy_x = nullptr, *psy_w = nullptr, *spike = nullptr;
     unsigned *psy_cand = nullptr, *psy_t0 = nullptr;
     Mp2Maskers *maskers = nullptr;
+    double *p2_energy = nullptr, *p2_phi = nullptr;
     tlb_side *side = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -126,6 +130,7 @@ struct tlb_batch {
     size_t chunk = 0;
     Slot slot[2];
     Mp2PsyTables *d_tables = nullptr;
+    Mp2Psy2Tables *d_tables2 = nullptr;
     uint64_t launches = 0;
     int last_slot = 0;
     bool profile = false;
@@ -156,12 +161,17 @@ int alloc_slot(tlb_batch *b, Slot &s)
     CU(cudaMalloc(&s.j_scale, fa * 96));
     CU(cudaMalloc(&s.smr, fa32 * 64 * sizeof(double)));
     const size_t items = fa * nch, tiles = (items + 31) / 32;
-    CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
-    CU(cudaMalloc(&s.psy_w, tiles * 512 * 32 * sizeof(double)));
-    CU(cudaMalloc(&s.psy_cand, items * 16 * sizeof(unsigned)));
-    CU(cudaMalloc(&s.psy_t0, items * 16 * sizeof(unsigned)));
-    CU(cudaMalloc(&s.spike, items * 32 * sizeof(double)));
-    CU(cudaMalloc(&s.maskers, items * sizeof(Mp2Maskers)));
+    if (b->P.psy == 2) {
+        CU(cudaMalloc(&s.p2_energy, (2 * fa + 2) * nch * 520 * sizeof(double)));
+        CU(cudaMalloc(&s.p2_phi, (2 * fa + 2) * nch * 520 * sizeof(double)));
+    } else {
+        CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
+        CU(cudaMalloc(&s.psy_w, tiles * 512 * 32 * sizeof(double)));
+        CU(cudaMalloc(&s.psy_cand, items * 16 * sizeof(unsigned)));
+        CU(cudaMalloc(&s.psy_t0, items * 16 * sizeof(unsigned)));
+        CU(cudaMalloc(&s.spike, items * 32 * sizeof(double)));
+        CU(cudaMalloc(&s.maskers, items * sizeof(Mp2Maskers)));
+    }
     CU(cudaMalloc(&s.side, fa * sizeof(tlb_side)));
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -173,6 +183,7 @@ void free_slot(Slot &s)
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
     cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
+    cudaFree(s.p2_energy); cudaFree(s.p2_phi);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s = Slot();
@@ -185,14 +196,17 @@ Mp2Chunk chunk_of(const tlb_batch *b, const Slot &s, const int16_t *pcm, long lo
     Mp2Chunk c;
     c.pcm = pcm; c.lo = lo; c.xpad = xpad; c.sb = s.sb; c.scalar_pre = s.scalar_pre; c.j_scale = s.j_scale;
     c.smr = s.smr; c.side = s.side; c.psy_x = s.psy_x; c.psy_w = s.psy_w; c.psy_cand = s.psy_cand; c.psy_t0 = s.psy_t0;
-    c.spike = s.spike; c.maskers = s.maskers; c.out = out; c.fa = fa; c.n_out = n_out;
+    c.spike = s.spike; c.maskers = s.maskers; c.p2_energy = s.p2_energy; c.p2_phi = s.p2_phi;
+    c.p2_first_block = lo == 0 ? 0 : -2; // at the stream start the blocks before the first frame are the zero state
+    c.out = out; c.fa = fa; c.n_out = n_out;
     return c;
 }
 
 int check_args(const tlb_batch *b, const void *pcm, size_t history, const void *out)
 {
     if (!b || !pcm || !out) return fail(TLB_E_ARG, "NULL argument");
-    if (history != 0 && history < (size_t)HALO_NEEDED) return fail(TLB_E_ARG, "history_samples must be 0 or >= 480");
+    if (history != 0 && history < (size_t)b->info.halo_samples)
+        return fail(TLB_E_ARG, "history_samples must be 0 or >= halo_samples (480; 1632 for psy model 2)");
     return 0;
 }
 
@@ -246,6 +260,24 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
             return fail(TLB_E_CUDA, "table upload failed");
         }
     }
+    if (P.psy == 2) {
+        static mp2_psy2_tables H; // host-side start-up tables, evaluated with libm as the reference does
+        static Mp2Psy2Tables D;
+        if (mp2_psy2_init(&H, (double)cfg->sample_rate)) { tlb_batch_destroy(b); return fail(TLB_E_PARAM, "psy-2 tables"); }
+        std::memset(&D, 0, sizeof D);
+        std::memcpy(D.s, H.s, sizeof D.s);
+        for (int j = 0; j < 64; j++) {
+            D.tmn[j] = H.tmn[j]; D.rnorm[j] = H.rnorm[j]; D.bmax_of[j] = H.bmax_of[j]; D.numlines[j] = H.numlines[j];
+        }
+        for (int j = 0; j <= 64; j++) D.first_line[j] = H.first_line[j];
+        for (int j = 0; j < 513; j++) D.partition[j] = (uint8_t)H.partition[j];
+        D.absthr_table = H.absthr_table;
+        if (cudaMalloc(&b->d_tables2, sizeof D) != cudaSuccess ||
+            cudaMemcpy(b->d_tables2, &D, sizeof D, cudaMemcpyHostToDevice) != cudaSuccess) {
+            tlb_batch_destroy(b);
+            return fail(TLB_E_CUDA, "psy-2 table upload failed");
+        }
+    }
     *out = b;
     return 0;
 }
@@ -259,6 +291,7 @@ void tlb_batch_destroy(tlb_batch *b)
         free_slot(s);
     }
     cudaFree(b->d_tables);
+    cudaFree(b->d_tables2);
     delete b;
 }
 
@@ -305,7 +338,7 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
                            (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
         if (use_xpad) CU(cudaMemcpyAsync(s.d_xpad, xpad + f0 * rec, fa * rec, cudaMemcpyHostToDevice, s.stream));
         Mp2Chunk c = chunk_of(b, s, s.d_pcm + HALO * nch, -(long)hist, use_xpad ? s.d_xpad : nullptr, s.d_out, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, s.stream, b->next_events());
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, b->d_tables2, s.stream, b->next_events());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + f0 * lg, s.d_out, n_out * lg, cudaMemcpyDeviceToHost, s.stream));
         s.last_fa = (int)fa;
@@ -341,7 +374,7 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
         const size_t hist = f0 * 1152 + history_samples;
         Mp2Chunk c = chunk_of(b, s, d_pcm + f0 * 1152 * nch, -(long)hist, use_xpad ? d_xpad + f0 * rec : nullptr,
                               d_out + f0 * lg, (int)fa, (int)n_out);
-        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, s.stream, b->next_events());
+        b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, b->d_tables2, s.stream, b->next_events());
         CU(cudaGetLastError());
         s.last_fa = (int)fa;
         b->last_slot = two ? (int)(k & 1) : 0;
@@ -382,6 +415,13 @@ int tlb_batch_kernel_times(tlb_batch *b, double *ms, uint64_t *launches)
 int tlb_kernel_count(void) { return MP2_N_KERNELS; }
 
 const char *tlb_kernel_name(int k) { return k >= 0 && k < MP2_N_KERNELS ? MP2_KERNEL_NAMES[k] : ""; }
+
+const char *tlb_batch_kernel_name(const tlb_batch *b, int k)
+{
+    static const char *const psy2_names[MP2_N_KERNELS] = {"k_filterbank", "k_spectrum2", "k_psy2", "", "k_alloc", "k_pack"};
+    if (k < 0 || k >= MP2_N_KERNELS) return "";
+    return b && b->P.psy == 2 ? psy2_names[k] : MP2_KERNEL_NAMES[k];
+}
 
 int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops)
 {

@@ -13,6 +13,7 @@ struct Mp2Params {
     int dab_ext, lg_frame, pad_len;
     int psy_freq, sub_size, cb_count;   // psy-1 table selectors (psycho_1.c:42-56)
     int bitrate_per_ch;                 // kbit/s per channel (psycho_1_threshold's ATH offset switch)
+    int psy;                            // psychoacoustic model: 1 or 2
 };
 
 // Per-stream lookup tables of the psychoacoustic model, built on the host at create time.
@@ -21,6 +22,16 @@ struct Mp2PsyTables {
     uint8_t band[512];   // FFT line -> critical band (critband.h boundaries); 255 outside every band
     uint8_t mm_j0[32];   // per subband: first threshold partition of psycho_1_minimum_mask's scan (255: past the end)
     uint8_t mm_j1[32];   // ... and one past its last partition
+};
+
+// Start-up tables of psychoacoustic model 2 (host-computed: mp2_psy2_init.h), device copy.
+struct Mp2Psy2Tables {
+    double s[64][64];     // spreading function, s[j][k]: partition k into partition j
+    double tmn[64], rnorm[64], bmax_of[64];
+    int numlines[64];
+    int first_line[65];   // partition p covers FFT lines first_line[p] .. first_line[p+1]-1
+    int absthr_table;
+    uint8_t partition[520];
 };
 
 // Surviving maskers of one (frame, channel), in the order psycho_1_threshold visits them.
@@ -46,7 +57,10 @@ struct Mp2Chunk {
     unsigned *psy_t0;       // [fa*nch][16] candidates passing the neighbourhood test on the unmodified spectrum
     double *spike;          // [fa*nch][32]
     Mp2Maskers *maskers;    // [fa*nch]
-    double *smr;            // [fa][2][32]
+    double *p2_energy;      // psy-2: [(2*fa+2)*nch][520] energy per block and channel, record (block+2)*nch+ch
+    double *p2_phi;         // psy-2: same layout, phase
+    long p2_first_block;    // psy-2: lowest block (relative to the chunk's first frame) that exists; earlier = zero state
+    double *smr;            // [ceil(fa/32)][64][32] frame-tile layout
     tlb_side *side;         // [fa]
     uint8_t *out;           // [n_out][lg_frame]
     int fa;                 // frames analysed
@@ -55,7 +69,8 @@ struct Mp2Chunk {
 
 // Launch the kernels of one chunk on `stream`; returns the number of launches issued.
 // ev: NULL, or MP2_N_KERNELS+1 events recorded before / between / after the kernels (per-kernel timing).
-int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const Mp2PsyTables *tables, cudaStream_t stream, cudaEvent_t *ev);
+int mp2_launch_chunk(const Mp2Params &p, const Mp2Chunk &c, const Mp2PsyTables *tables, const Mp2Psy2Tables *tables2,
+                     cudaStream_t stream, cudaEvent_t *ev);
 constexpr int MP2_N_KERNELS = 6;
 extern const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS];
 

@@ -28,9 +28,9 @@ struct Stream {
     int pad_len = 0;
     tlb_batch *enc = nullptr;
     tlb_info info{};
-    std::vector<int16_t> pcm;     // [1152 previous | 1152 current] * nch, interleaved
+    std::vector<int16_t> pcm;     // [2304 previous | 1152 current] * nch, interleaved (psy-2 looks 1632 samples back)
     std::vector<uint8_t> held;    // bytes still in the reference's bit buffer, oldest first
-    std::vector<uint8_t> frame, rec;
+    std::vector<uint8_t> frame, rec, rec_prev;
     long frame_num = 0;
     bool failed = false;
 } g;
@@ -51,9 +51,10 @@ bool open_encoder()
         g.failed = true;
         return false;
     }
-    g.pcm.assign((size_t)2 * 1152 * g.info.nch, 0);
+    g.pcm.assign((size_t)3 * 1152 * g.info.nch, 0);
     g.frame.resize((size_t)g.info.lg_frame);
     g.rec.assign((size_t)g.pad_len + 1, 0);
+    g.rec_prev.assign((size_t)g.pad_len + 1, 0);
     g.held.reserve(BUFFER_SIZE + 2048);
     return true;
 }
@@ -98,8 +99,8 @@ int toolame_set_psy_model(int new_model)
         std::fprintf(stderr, "libtoolame-dab: Invalid PSY model %d\n", new_model);
         return 1;
     }
-    if (new_model != 1) {
-        std::fprintf(stderr, "libtoolame-b200: PSY model %d is not built (only model 1)\n", new_model);
+    if (new_model != 1 && new_model != 2) {
+        std::fprintf(stderr, "libtoolame-b200: PSY model %d is not built (models 1 and 2 are)\n", new_model);
         return 1;
     }
     g.psy = new_model;
@@ -151,7 +152,7 @@ int toolame_encode_frame(short buffer[2][1152], unsigned char *xpad_data, size_t
     const int nch = g.info.nch;
     const size_t lg = (size_t)g.info.lg_frame;
     g.frame_num++;
-    int16_t *cur = g.pcm.data() + (size_t)1152 * nch;
+    int16_t *cur = g.pcm.data() + (size_t)2304 * nch;
     for (int i = 0; i < 1152; i++)
         for (int ch = 0; ch < nch; ch++) cur[i * nch + ch] = buffer[ch][i];
     const uint8_t *rec = nullptr;
@@ -164,12 +165,34 @@ int toolame_encode_frame(short buffer[2][1152], unsigned char *xpad_data, size_t
             rec = g.rec.data();
         }
     }
-    const int rc = tlb_batch_encode(g.enc, cur, 1, g.frame_num == 1 ? 0 : 1152, 0, rec, g.frame.data());
+    // History handed to the batch encoder: 0 at the stream start (the reference's zero state), otherwise what is
+    // kept here (1152 samples after the first frame, 2304 from the third on).  Psy model 2 looks 1632 samples
+    // back, more than one frame: its second frame is encoded together with the first, from the stream start.
+    int rc;
+    if (g.frame_num == 2 && g.psy == 2) {
+        std::vector<uint8_t> two(2 * lg), recs;
+        const uint8_t *rp = nullptr;
+        if (g.pad_len) {
+            recs.assign(g.rec_prev.begin(), g.rec_prev.end());
+            if (rec) recs.insert(recs.end(), g.rec.begin(), g.rec.end());
+            else recs.resize(2 * ((size_t)g.pad_len + 1), 0);
+            rp = recs.data();
+        }
+        rc = tlb_batch_encode(g.enc, cur - (size_t)1152 * nch, 2, 0, 0, rp, two.data());
+        std::memcpy(g.frame.data(), two.data() + lg, lg);
+    } else {
+        const size_t hist = g.frame_num > 2 ? 2304 : (size_t)(g.frame_num - 1) * 1152;
+        rc = tlb_batch_encode(g.enc, cur, 1, hist, 0, rec, g.frame.data());
+    }
+    if (g.pad_len) {
+        if (rec) g.rec_prev = g.rec;
+        else g.rec_prev.assign((size_t)g.pad_len + 1, 0);
+    }
     if (rc) {
         std::fprintf(stderr, "libtoolame-b200: encode failed: %s\n", tlb_last_error());
         return 0;
     }
-    std::memmove(g.pcm.data(), cur, (size_t)1152 * nch * sizeof(int16_t));
+    std::memmove(g.pcm.data(), g.pcm.data() + (size_t)1152 * nch, (size_t)2304 * nch * sizeof(int16_t));
     // this frame's ScF-CRC also replaces the previous frame's, which is still held (ref: toolame.c:527-539)
     if (g.frame_num > 1 && g.held.size() >= lg) {
         const size_t ext = (size_t)g.info.dab_ext;

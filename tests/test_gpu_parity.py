@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _enc(fs, mode, br, pad_len=0, chunk=0):
+def _enc(fs, mode, br, pad_len=0, chunk=0, psy=1):
     import odr_audioenc_b200 as tl
-    return tl.BatchEncoder(fs, mode, br, 1, pad_len, 0, chunk)
+    return tl.BatchEncoder(fs, mode, br, psy, pad_len, 0, chunk)
 
 
 @pytest.mark.parametrize("cfg,sig,n", cases.GOLDEN, ids=["%s-%s" % (c, s) for c, s, _ in cases.GOLDEN])
@@ -83,16 +83,16 @@ def test_chunks_and_ranges_are_seamless(cfg):
         assert np.array_equal(got, ref[f0 * lg:f1 * lg]), (f0, f1)
 
 
-@pytest.mark.parametrize("cfg,sig", [("Bj", "S1"), ("C", "S8"), ("T2", "S2")])
-def test_streaming_dropin_matches_chunking_and_bytes(cfg, sig):
+@pytest.mark.parametrize("cfg,sig,psy", [("Bj", "S1", 1), ("C", "S8", 1), ("T2", "S2", 1), ("E1", "S8", 2)])
+def test_streaming_dropin_matches_chunking_and_bytes(cfg, sig, psy):
     """toolame_init/set_*/encode_frame/finish: same bytes, same return sizes as the reference's bit buffer gives
     (0 or 4096-(lg_frame+4): bitstream.c:46-71)"""
     import odr_audioenc_b200 as tl
     n = 30
     fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
-    c = oracle.configure(fs, mode, br)
+    c = oracle.configure(fs, mode, br, psy)
     ref, _ = oracle.encode(c, pcm)
-    s = tl.ToolameStream(fs, mode, br)
+    s = tl.ToolameStream(fs, mode, br, psy)
     chunks, sizes = [], []
     for f in range(n):
         b = s.encode_frame(pcm[f * 1152:(f + 1) * 1152])
@@ -128,3 +128,52 @@ def test_large_batch_properties():
     c = oracle.configure(48000, "j", 192)
     ref, _ = oracle.encode(c, pcm, 3000, 3100)
     assert np.array_equal(out[3000:3100].ravel(), ref)
+
+
+# ---- psychoacoustic model 2 (BASELINE config 5: 48 kHz 256 kbit/s joint stereo, inter-frame state as a halo)
+ALL_PSY2 = cases.GOLDEN_PSY2
+
+
+@pytest.mark.parametrize("cfg,sig,n", ALL_PSY2, ids=["%s-%s" % (c, s) for c, s, _ in ALL_PSY2])
+def test_psy2_bytes_equal_reference_golden(cfg, sig, n):
+    g = np.load(os.path.join(GOLD, "psy2_%s_%s.npz" % (cfg, sig)))
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    out = _enc(fs, mode, br, psy=2).encode(pcm)
+    assert np.array_equal(out, g["bytes"])
+
+
+@pytest.mark.parametrize("cfg,sig", [("E1", "S1"), ("E1", "S8"), ("E1", "S4"), ("C", "S8"), ("Bs", "S2"), ("M48", "S6")])
+def test_psy2_stages_equal_oracle(cfg, sig):
+    """SMR within 1e-9 dB of the oracle (device cos/sin/atan2/log/exp vs glibc), decisions and bytes identical"""
+    import odr_audioenc_b200 as tl
+    n = 60
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    c = oracle.configure(fs, mode, br, 2)
+    ref, tap = oracle.encode(c, pcm, taps=True)
+    e = _enc(fs, mode, br, psy=2)
+    out = e.encode(pcm)
+    nch, sbl = c.nch, c.sblimit
+    smr = e.tap(tl.TAP_SMR, n)[:, :nch, :sbl]
+    d = np.abs(smr - tap["smr"][:, :nch, :sbl])
+    assert (d > 1e-9).mean() <= 0.01, "SMR: %d of %d values off by more than 1e-9 dB (max %g)" % ((d > 1e-9).sum(), d.size, d.max())
+    side = e.tap(tl.TAP_SIDE, n)
+    assert np.array_equal(side["bit_alloc"][:, :nch, :sbl], tap["bit_alloc"][:, :nch, :sbl])
+    assert np.array_equal(out, ref)
+
+
+def test_psy2_ranges_need_the_two_block_halo():
+    """mid-stream ranges with 1632 samples of history reproduce the one-shot stream; chunk boundaries are seamless"""
+    n = 40
+    fs, mode, br, pcm, _, _ = cases.make_case("E1", "S8", n)
+    c = oracle.configure(fs, mode, br, 2)
+    ref, _ = oracle.encode(c, pcm)
+    lg = c.lg_frame
+    e = _enc(fs, mode, br, chunk=7, psy=2)
+    assert e.halo_samples == 1632
+    assert np.array_equal(e.encode(pcm), ref)
+    for f0, f1 in ((0, 9), (9, 31), (31, 40)):
+        hist = min(f0 * 1152, 2 * 1152)
+        has_next = f1 < n
+        seg = pcm[f0 * 1152 - hist:(f1 + has_next) * 1152]
+        got = e.encode(seg, history=hist, has_next=has_next)
+        assert np.array_equal(got, ref[f0 * lg:f1 * lg]), (f0, f1)
