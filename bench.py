@@ -26,20 +26,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-FS, MODE, KBPS, NCH = 48000, "j", 192, 2   # odr-audioenc's default mode for 2 channels is joint stereo
+# BASELINE.json configs: B = configs[1] (the metric's configuration, the default), C = configs[2], E = configs[4]
+CONFIGS = {"B": (48000, "j", 192, 2, 1, "MP2 DAB 192 kbit/s 48 kHz stereo (mode j), psy model 1"),
+           "C": (24000, "m", 64, 1, 1, "MP2 DAB 64 kbit/s 24 kHz mono (LSF tables), psy model 1"),
+           "E": (48000, "j", 256, 2, 2, "MP2 DAB 256 kbit/s 48 kHz joint stereo, psy model 2")}
+FS, MODE, KBPS, NCH, PSY, WORKLOAD = CONFIGS["B"]   # odr-audioenc's default mode for 2 channels is joint stereo
 METRIC = "MP2 audio-seconds encoded/sec"
 UNIT = "audio-s/s"
+KERNEL_ALG = {}
 
-# algorithmic bytes and FP64 flops per frame of this config (PCM in + frame out; data-independent flops)
-ALG_BYTES_PER_FRAME = NCH * 1152 * 2 + 3 * KBPS
-KERNEL_ALG = {  # per frame: (bytes the kernel must move, FP64 flops it must do), stated in DESIGN.md
-    "k_filterbank": (NCH * 1152 * 2 + NCH * 1152 * 8 + 192 + 96, NCH * 74844 + 2304),
-    "k_spectrum": (NCH * (1024 * 2 + 2 * 512 * 8 + 128 + 256), NCH * 27334),
-    "k_label": (NCH * (2 * 512 * 8 + 128 + 1128), 0),
-    "k_threshold": (NCH * (1128 + 256 + 256) + 192, 0),
-    "k_alloc": (192 + NCH * 32 * 8 + 336, 0),
-    "k_pack": (NCH * 1152 * 8 + 336 + 96 + 3 * KBPS, NCH * 3888),
-}
+
+def select_config(name):
+    """algorithmic bytes and FP64 flops per frame (data-independent flops), per kernel: the bytes
+    a kernel must move for one frame and the FP64 operations it must do."""
+    global FS, MODE, KBPS, NCH, PSY, WORKLOAD, KERNEL_ALG
+    FS, MODE, KBPS, NCH, PSY, WORKLOAD = CONFIGS[name]
+    lg = (3 if FS == 48000 else 6) * KBPS
+    sbl = 27 if FS == 48000 else 30
+    KERNEL_ALG = {
+        "k_filterbank": (NCH * 1152 * 2 + NCH * 1152 * 8 + 192 + 96, NCH * 74844 + (2304 if MODE == "j" else 0)),
+        "k_spectrum": (NCH * (1024 * 2 + 2 * 512 * 8 + 128 + 256), NCH * 27334),
+        "k_label": (NCH * (2 * 512 * 8 + 128 + 1128), 0),
+        "k_threshold": (NCH * (1128 + 256 + 256) + 192, 0),
+        "k_spectrum2": (NCH * 2 * (1024 * 2 + 2 * 513 * 8), NCH * 2 * (1024 + 20488 + 2046)),
+        "k_psy2": (NCH * (4 * 2 * 513 * 8 + 256), NCH * 2 * 513 * 40),
+        "k_alloc": (192 + NCH * 32 * 8 + 336, 0),
+        "k_pack": (NCH * 1152 * 8 + 336 + 96 + lg, NCH * sbl * 36 * 4),
+    }
+
+
+select_config("B")
 
 
 def synth_pcm_torch(n_frames, seed, device):
@@ -117,7 +133,7 @@ def cpu_reference_run(seconds_audio, n_procs, steps=1, warmup=0):
         pcm.tofile(pin)
         if os.path.exists(ref_driver):
             kind = "reference"
-            cmd = [ref_driver, str(FS), MODE, str(KBPS), "1", "0", pin, os.path.join(td, "out%d.mp2"), "--bench"]
+            cmd = [ref_driver, str(FS), MODE, str(KBPS), str(PSY), "0", pin, os.path.join(td, "out%d.mp2"), "--bench"]
 
             def one_step():
                 t0 = time.perf_counter()
@@ -145,7 +161,7 @@ def _oracle_worker(pin):
     import numpy as np
     import oracle
     pcm = np.fromfile(pin, dtype=np.int16).reshape(-1, NCH)
-    c = oracle.configure(FS, MODE, KBPS)
+    c = oracle.configure(FS, MODE, KBPS, PSY)
     t0 = time.perf_counter()
     oracle.encode(c, pcm)
     return time.perf_counter() - t0
@@ -165,7 +181,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MP2 DAB 192 kbit/s 48 kHz stereo (mode j), psy model 1; per step a bounded sample of the "
+        "config": {"workload": WORKLOAD + "; per step a bounded sample of the "
                                "10 h batch: %.0f s of audio per host core, %d cores" % (n_frames * 1152 / FS, cores)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "%d processes x %d frames (%.0f s) of signal S1, encode loop only" % (cores, n_frames, n_frames * 1152 / FS)},
@@ -182,6 +198,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hours", type=float, default=10.0, help="audio per GPU per step (BASELINE config: 10 h)")
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="B = BASELINE configs[1] (default), C = configs[2], E = configs[4]")
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--cpu-sample-seconds", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,6 +206,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 0)
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -215,7 +233,7 @@ def main():
         torch.cuda.synchronize()
 
     n_frames = int(round(args.hours * 3600 * FS / 1152))
-    enc = tl.BatchEncoder(FS, MODE, KBPS, 1, 0, local, args.chunk_frames)
+    enc = tl.BatchEncoder(FS, MODE, KBPS, PSY, 0, local, args.chunk_frames)
     lg = enc.lg_frame
     L = tl.lib()
 
@@ -314,15 +332,16 @@ def main():
     import oracle
     chk_f0, chk_n = n_frames // 2, 64
     seg = d_pcm[(chk_f0 * 1152 - 1152):(chk_f0 + chk_n + 1) * 1152].cpu().numpy()
-    ocfg = oracle.configure(FS, MODE, KBPS)
+    ocfg = oracle.configure(FS, MODE, KBPS, PSY)
     want, _ = oracle.encode(ocfg, np.concatenate([np.zeros((0, NCH), np.int16), seg]), 1, 1 + chk_n)
     # (the oracle starts its history at the segment start; one leading frame gives frames 1.. their true 480-sample halo)
     got = d_out[chk_f0 * lg:(chk_f0 + chk_n) * lg].cpu().numpy()
     parity_frames_equal = int((got.reshape(chk_n, -1) == want.reshape(chk_n, -1)).all(axis=1).sum())
 
     # ---- roofline of the dominant kernel
-    L.tlb_kernel_name.restype = C.c_char_p
-    names = [L.tlb_kernel_name(k).decode() for k in range(NK)]
+    L.tlb_batch_kernel_name.restype = C.c_char_p
+    L.tlb_batch_kernel_name.argtypes = [C.c_void_p, C.c_int]
+    names = [L.tlb_batch_kernel_name(enc._h, k).decode() or "unused%d" % k for k in range(NK)]
     per_kernel = {}
     total_ms = sum(ms[k] for k in range(NK)) or 1.0
     for k in range(NK):
@@ -337,7 +356,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    kb, kf = KERNEL_ALG[names[top]]
+    kb, kf = KERNEL_ALG.get(names[top], (0, 0))
     dur_s = per_kernel[names[top]]["avg_ms"] * 1e-3
     achieved_gbs = kb * frames_per_launch / dur_s / 1e9
     dfma, dmuladd = C.c_double(), C.c_double()
@@ -361,7 +380,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MP2 DAB 192 kbit/s 48 kHz stereo (mode j), psy model 1, %.3g h synthetic PCM batch per GPU "
+        "config": {"workload": WORKLOAD + ", %.3g h synthetic PCM batch per GPU "
                                "(%d frames); inputs (%.2f GB) larger than L2" % (args.hours, n_frames, pcm_bytes / 1e9),
                    "frames_per_gpu": n_frames, "x_realtime_per_gpu": value / world},
         "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),

@@ -21,6 +21,9 @@ import signals  # noqa: E402
 
 CASES = [("Bj", "S1"), ("Bj", "S2"), ("Bj", "S8"), ("Bj", "S6"), ("Bj", "S4"), ("Bj", "S7"), ("Bs", "S1"), ("Bs", "S8"),
          ("A", "S1"), ("A", "S8"), ("C", "S1"), ("C", "S8"), ("C", "S2"), ("T2j", "S8"), ("M48", "S1"), ("E1", "S8")]
+PSY = int(os.environ.get("SWEEP_PSY", "1"))
+if PSY == 2:
+    CASES = [("E1", "S1"), ("E1", "S8"), ("E1", "S2"), ("E1", "S6"), ("E1", "S4"), ("Bs", "S8"), ("C", "S8"), ("A", "S1")]
 SEG = 500  # frames per oracle work item
 
 
@@ -29,7 +32,7 @@ def _oracle_seg(job):
     fs, mode, br = cases.CONFIGS[cfg_name]
     nch = 1 if mode == "m" else 2
     pcm = signals.make(sig, n, nch, fs)
-    c = oracle.configure(fs, mode, br)
+    c = oracle.configure(fs, mode, br, PSY)
     out, tap = oracle.encode(c, pcm, f0, f1, taps=True)
     return f0, out, tap["smr"].copy(), tap["bit_alloc"].copy(), tap["scalar"].copy()
 
@@ -45,7 +48,7 @@ def main():
             nch = 1 if mode == "m" else 2
             t0 = time.time()
             pcm = signals.make(sig, n, nch, fs)
-            enc = tl.BatchEncoder(fs, mode, br, chunk_frames=n + 1)
+            enc = tl.BatchEncoder(fs, mode, br, PSY, chunk_frames=n + 1)
             got = enc.encode(pcm).reshape(n, -1)
             smr = enc.tap(tl.TAP_SMR, n)
             side = enc.tap(tl.TAP_SIDE, n)
@@ -65,7 +68,7 @@ def main():
                         first_stage["bit_alloc"] += 1
                     else:
                         first_stage["bytes_only"] += 1
-            rec = {"config": cfg_name, "signal": sig, "frames": n, "frames_differing": len(bad_frames),
+            rec = {"config": cfg_name, "signal": sig, "psy": PSY, "frames": n, "frames_differing": len(bad_frames),
                    "frames_with_smr_off_by_1e-9": smr_off, "first_departure": first_stage,
                    "examples": sorted(bad_frames)[:8], "seconds": round(time.time() - t0, 1)}
             print(json.dumps(rec), flush=True)
