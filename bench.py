@@ -191,6 +191,108 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+ENSEMBLE = [(48000, "j", 192)] * 6 + [(48000, "j", 160)] * 4 + [(48000, "j", 128)] * 4 + [(48000, "j", 112)] * 2 + \
+           [(48000, "m", 96)] * 2   # BASELINE configs[3]: 18 MP2 services, mixed 96-192 kbit/s
+
+
+def run_ensemble(args):
+    """--config D: the 18-service ensemble, `--hours` of audio per service, sharded by whole services across the
+    ranks (odr_audioenc_b200.sharding.service_shards: LPT by a bitrate-weighted cost).  Fixed total work: strong
+    scaling.  Device-resident value and end-to-end (pinned host buffers) like the main mode."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import odr_audioenc_b200 as tl
+    from odr_audioenc_b200 import sharding
+    global FS, NCH
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_frames = int(round(args.hours * 3600 * 48000 / 1152))
+    plan = sharding.service_shards([(fs, 1 if m == "m" else 2, br, n_frames) for fs, m, br in ENSEMBLE], world)
+    mine = plan[rank]
+    L = tl.lib()
+    encs, work = {}, []
+    for i in mine:
+        fs, mode, br = ENSEMBLE[i]
+        key = (fs, mode, br)
+        if key not in encs:
+            encs[key] = tl.BatchEncoder(fs, mode, br, 1, 0, local, args.chunk_frames or 148 * 256)
+        e = encs[key]
+        FS, NCH = fs, e.nch
+        d_pcm = synth_pcm_torch(n_frames, 5000 + i, dev)
+        d_out = torch.empty(n_frames * e.lg_frame, dtype=torch.uint8, device=dev)
+        work.append((e, d_pcm, d_out))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        for e, d_pcm, d_out in work:
+            e.encode_device(d_pcm.data_ptr(), n_frames, 0, False, None, d_out.data_ptr())
+        for e in encs.values():
+            e.sync()
+
+    h_bufs = []
+    for e, d_pcm, d_out in work:
+        hp, ho = L.tlb_host_alloc(d_pcm.numel() * 2), L.tlb_host_alloc(d_out.numel())
+        h_pcm = np.ctypeslib.as_array((C.c_int16 * d_pcm.numel()).from_address(hp)).reshape(-1, e.nch)
+        h_out = np.ctypeslib.as_array((C.c_uint8 * d_out.numel()).from_address(ho))
+        torch.from_numpy(h_pcm).copy_(d_pcm)
+        h_bufs.append((h_pcm, h_out))
+    L.tlb_batch_encode_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+
+    def step_host():
+        for (e, _, _), (h_pcm, h_out) in zip(work, h_bufs):
+            L.tlb_batch_encode_async(e._h, h_pcm.ctypes.data, n_frames, 0, 0, None, h_out.ctypes.data)
+        for e in encs.values():
+            e.sync()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        barrier()
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+
+    launches0 = sum(e.launches for e in encs.values())
+    t_dev = timed(step_device)
+    launches = (sum(e.launches for e in encs.values()) - launches0) // (args.steps + args.warmup)
+    t_host = timed(step_host)
+    same = all(bool(torch.equal(torch.from_numpy(h_out[:4096]).to(dev), d_out[:4096])) for (_, _, d_out), (_, h_out) in zip(work, h_bufs))
+    if rank == 0:
+        audio = len(ENSEMBLE) * n_frames * 1152 / 48000
+        print(json.dumps({
+            "metric": METRIC, "value": audio * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "DAB ensemble: 18 MP2 services x %.3g h, 6x192 4x160 4x128 2x112 kbit/s joint stereo + 2x96 mono, "
+                                   "psy model 1, whole services per GPU (LPT)" % args.hours, "plan": plan},
+            "e2e": {"value": audio * args.steps / t_host, "unit": UNIT,
+                    "h2d_bytes_per_step": sum(int(n_frames * 1152 * (1 if m == "m" else 2) * 2) for _, m, _ in ENSEMBLE),
+                    "d2h_bytes_per_step": sum(int(n_frames * 3 * br) for _, _, br in ENSEMBLE)},
+            "gpu_launches": int(launches * args.steps), "host_equals_device_outputs": same}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,7 +300,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hours", type=float, default=10.0, help="audio per GPU per step (BASELINE config: 10 h)")
-    ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="B = BASELINE configs[1] (default), C = configs[2], E = configs[4]")
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS) + ["D"], help="B = BASELINE configs[1] (default), C = configs[2], E = configs[4]")
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--cpu-sample-seconds", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -206,6 +308,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 0)
+    if args.config == "D":
+        if args.impl == "reference":
+            raise SystemExit("--config D has no reference arm (use the default config)")
+        if args.hours == 10.0:
+            args.hours = 1.0  # BASELINE configs[3]: 1 h per service
+        return run_ensemble(args)
     select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)

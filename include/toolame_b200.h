@@ -87,6 +87,23 @@ TLB_API const char *tlb_last_error(void);
 TLB_API int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples,
                      int has_next, const uint8_t *xpad, uint8_t *out);
 
+/* As tlb_batch_encode, but returns once the work is queued; tlb_batch_sync waits.  With pageable host memory the
+ * copies still block; pinned memory (tlb_host_alloc) makes the call fully asynchronous. */
+TLB_API int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples,
+                           int has_next, const uint8_t *xpad, uint8_t *out);
+
+/* Many services (streams) at once, each a whole stream from its start: the multi-service form of the loop in
+ * src/odr-audioenc.cpp:819-1276 run once per service.  Services of different configurations run side by side on
+ * the GPU.  xpad may be NULL per service; out receives n_frames * lg_frame bytes per service. */
+typedef struct {
+    tlb_config cfg;
+    const int16_t *pcm;   /* interleaved s16, n_frames * 1152 * nch samples */
+    size_t n_frames;
+    const uint8_t *xpad;  /* NULL or n_frames records of pad_len + 1 bytes */
+    uint8_t *out;
+} tlb_service;
+TLB_API int tlb_encode_services(const tlb_service *sv, size_t n, int device, size_t chunk_frames);
+
 /* Same, with pcm / xpad / out already in DEVICE memory of the encoder's GPU; d_pcm must be readable
  * from d_pcm - history_samples*nch.  Asynchronous on the encoder's stream; tlb_batch_sync waits. */
 TLB_API int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames, size_t history_samples,

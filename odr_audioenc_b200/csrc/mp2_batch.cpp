@@ -313,8 +313,8 @@ int tlb_batch_sync(tlb_batch *b)
     return 0;
 }
 
-int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples, int has_next,
-                     const uint8_t *xpad, uint8_t *out)
+int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples, int has_next,
+                           const uint8_t *xpad, uint8_t *out)
 {
     int rc = check_args(b, pcm, history_samples, out);
     if (rc) return rc;
@@ -344,8 +344,45 @@ int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t h
         s.last_fa = (int)fa;
         b->last_slot = (int)(k & 1);
     }
-    for (auto &s : b->slot) CU(cudaStreamSynchronize(s.stream));
     return 0;
+}
+
+int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples, int has_next,
+                     const uint8_t *xpad, uint8_t *out)
+{
+    const int rc = tlb_batch_encode_async(b, pcm, n_frames, history_samples, has_next, xpad, out);
+    return rc ? rc : tlb_batch_sync(b);
+}
+
+int tlb_encode_services(const tlb_service *sv, size_t n, int device, size_t chunk_frames)
+{
+    if (!sv && n) return fail(TLB_E_ARG, "NULL argument");
+    // one encoder per distinct configuration; services of one configuration queue on the same encoder, different
+    // configurations run side by side on their own streams
+    std::vector<tlb_batch *> enc;
+    std::vector<tlb_config> cfgs;
+    int rc = 0;
+    for (size_t i = 0; i < n && !rc; i++) {
+        size_t e = 0;
+        for (; e < cfgs.size(); e++)
+            if (!std::memcmp(&cfgs[e], &sv[i].cfg, sizeof(tlb_config))) break;
+        if (e == cfgs.size()) {
+            tlb_batch *b = nullptr;
+            rc = tlb_batch_create(&b, &sv[i].cfg, device, chunk_frames ? chunk_frames : 148 * 128);
+            if (rc) break;
+            enc.push_back(b);
+            cfgs.push_back(sv[i].cfg);
+        }
+        rc = tlb_batch_encode_async(enc[e], sv[i].pcm, sv[i].n_frames, 0, 0, sv[i].xpad, sv[i].out);
+    }
+    for (auto b : enc) {
+        const int r2 = tlb_batch_sync(b);
+        if (!rc) rc = r2;
+    }
+    const std::string err = g_err;
+    for (auto b : enc) tlb_batch_destroy(b);
+    if (rc) g_err = err;
+    return rc;
 }
 
 int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames, size_t history_samples, int has_next,

@@ -177,3 +177,21 @@ def test_psy2_ranges_need_the_two_block_halo():
         seg = pcm[f0 * 1152 - hist:(f1 + has_next) * 1152]
         got = e.encode(seg, history=hist, has_next=has_next)
         assert np.array_equal(got, ref[f0 * lg:f1 * lg]), (f0, f1)
+
+
+def test_ensemble_of_services_in_one_call():
+    """BASELINE config 4 in miniature: services of mixed rates / modes through tlb_encode_services"""
+    import odr_audioenc_b200 as tl
+    import signals
+    spec = [(48000, "j", 192, "S1"), (48000, "j", 160, "S8"), (48000, "j", 128, "S2"), (48000, "j", 112, "S6"),
+            (48000, "m", 96, "S1"), (48000, "j", 192, "S4"), (24000, "m", 64, "S8"), (48000, "s", 96, "S8")]
+    n = 37
+    sv = []
+    for fs, mode, br, sig in spec:
+        nch = 1 if mode == "m" else 2
+        sv.append(dict(sample_rate=fs, mode=mode, bitrate=br, pcm=signals.make(sig, n, nch, fs)))
+    outs = tl.encode_services(sv, chunk_frames=16)
+    for s, got in zip(sv, outs):
+        c = oracle.configure(s["sample_rate"], s["mode"], s["bitrate"])
+        want, _ = oracle.encode(c, s["pcm"])
+        assert np.array_equal(got, want), (s["sample_rate"], s["mode"], s["bitrate"])
