@@ -265,7 +265,8 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
         static Mp2Psy2Tables D;
         if (mp2_psy2_init(&H, (double)cfg->sample_rate)) { tlb_batch_destroy(b); return fail(TLB_E_PARAM, "psy-2 tables"); }
         std::memset(&D, 0, sizeof D);
-        std::memcpy(D.s, H.s, sizeof D.s);
+        for (int j = 0; j < 64; j++)
+            for (int k = 0; k < 64; k++) D.sT[k][j] = H.s[j][k];
         for (int j = 0; j < 64; j++) {
             D.tmn[j] = H.tmn[j]; D.rnorm[j] = H.rnorm[j]; D.bmax_of[j] = H.bmax_of[j]; D.numlines[j] = H.numlines[j];
         }

@@ -26,7 +26,7 @@ struct Mp2PsyTables {
 
 // Start-up tables of psychoacoustic model 2 (host-computed: mp2_psy2_init.h), device copy.
 struct Mp2Psy2Tables {
-    double s[64][64];     // spreading function, s[j][k]: partition k into partition j
+    double sT[64][64];    // spreading function transposed: sT[k][j] = s[j][k], partition k into partition j
     double tmn[64], rnorm[64], bmax_of[64];
     int numlines[64];
     int first_line[65];   // partition p covers FFT lines first_line[p] .. first_line[p+1]-1
