@@ -110,6 +110,17 @@ TLB_API int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n
                             int has_next, const uint8_t *d_xpad, uint8_t *d_out);
 TLB_API int tlb_batch_sync(tlb_batch *b);
 
+/* The step before the encoder in odr-audioenc's loop, on the device (src/odr-audioenc.cpp:1020-1055): gain
+ * correction of interleaved s16 PCM in place (gain_db = 0 leaves it untouched) and the per-frame peak levels
+ * d_peaks[frame][2] = (left, right), computed on (left, right) sample pairs also in mono, as the reference does.
+ * Asynchronous on the encoder's stream (the one tlb_batch_encode_device uses), so it can be queued right before it. */
+TLB_API int tlb_batch_gain_peak_device(tlb_batch *b, int16_t *d_pcm, size_t n_frames, double gain_db, int16_t *d_peaks);
+
+/* The same for the host-buffer entry points: from now on tlb_batch_encode / _async apply gain_db on the device to
+ * the staged PCM (the caller's buffer is not modified) and, if peaks is not NULL, store the per-frame peak levels
+ * peaks[frame][2] there (frame counted from the first frame of each encode call).  gain_db = 0, peaks = NULL: off. */
+TLB_API int tlb_batch_set_gain(tlb_batch *b, double gain_db, int16_t *peaks);
+
 /* CUDA stream (cudaStream_t) the device-resident calls run on, for event timing by the caller. */
 TLB_API void *tlb_batch_stream(tlb_batch *b);
 /* Number of kernel launches issued by this encoder so far. */

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -114,6 +115,7 @@ struct Slot {
     unsigned *psy_cand = nullptr, *psy_t0 = nullptr;
     Mp2Maskers *maskers = nullptr;
     double *p2_energy = nullptr, *p2_phi = nullptr;
+    int16_t *d_peaks = nullptr; // [fa + 1][2]
     tlb_side *side = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -134,6 +136,8 @@ struct tlb_batch {
     uint64_t launches = 0;
     int last_slot = 0;
     bool profile = false;
+    double gain_db = 0.0;        // host-buffer path: gain applied on the device before encoding
+    int16_t *h_peaks = nullptr;  // host-buffer path: per-frame (left, right) peaks of the next encode calls
     std::vector<cudaEvent_t> prof_events; // MP2_N_KERNELS + 1 per profiled chunk
     cudaEvent_t *next_events()
     {
@@ -173,6 +177,7 @@ int alloc_slot(tlb_batch *b, Slot &s)
         CU(cudaMalloc(&s.maskers, items * sizeof(Mp2Maskers)));
     }
     CU(cudaMalloc(&s.side, fa * sizeof(tlb_side)));
+    CU(cudaMalloc(&s.d_peaks, (fa + 1) * 2 * sizeof(int16_t)));
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     return 0;
@@ -183,7 +188,7 @@ void free_slot(Slot &s)
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
     cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
-    cudaFree(s.p2_energy); cudaFree(s.p2_phi);
+    cudaFree(s.p2_energy); cudaFree(s.p2_phi); cudaFree(s.d_peaks);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s = Slot();
@@ -338,6 +343,15 @@ int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, si
         CU(cudaMemcpyAsync(s.d_pcm + (HALO - hist) * nch, pcm + (f0 * 1152 - hist) * nch,
                            (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
         if (use_xpad) CU(cudaMemcpyAsync(s.d_xpad, xpad + f0 * rec, fa * rec, cudaMemcpyHostToDevice, s.stream));
+        if (b->gain_db != 0.0 || b->h_peaks) { // ref: src/odr-audioenc.cpp:1020-1055, here per staged chunk
+            const double linear = std::pow(10.0, b->gain_db / 20.0);
+            if (hist && linear != 1.0) // the history samples are re-staged from the caller's (un-gained) buffer
+                mp2_launch_gain_peak_pairs(s.d_pcm + (HALO - hist) * nch, 1, (int)(hist * nch / 2), linear, s.d_peaks + 2 * fa, s.stream);
+            mp2_launch_gain_peak(s.d_pcm + HALO * nch, (long)fa, (int)nch, linear, s.d_peaks, s.stream);
+            b->launches += hist && linear != 1.0 ? 2 : 1;
+            if (b->h_peaks)
+                CU(cudaMemcpyAsync(b->h_peaks + 2 * f0, s.d_peaks, n_out * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
+        }
         Mp2Chunk c = chunk_of(b, s, s.d_pcm + HALO * nch, -(long)hist, use_xpad ? s.d_xpad : nullptr, s.d_out, (int)fa, (int)n_out);
         b->launches += (uint64_t)mp2_launch_chunk(b->P, c, b->d_tables, b->d_tables2, s.stream, b->next_events());
         CU(cudaGetLastError());
@@ -421,6 +435,26 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
         CU(cudaEventRecord(b->slot[1].done, b->slot[1].stream));
         CU(cudaStreamWaitEvent(b->slot[0].stream, b->slot[1].done, 0));
     }
+    return 0;
+}
+
+int tlb_batch_set_gain(tlb_batch *b, double gain_db, int16_t *peaks)
+{
+    if (!b) return fail(TLB_E_ARG, "NULL argument");
+    b->gain_db = gain_db;
+    b->h_peaks = peaks;
+    return 0;
+}
+
+int tlb_batch_gain_peak_device(tlb_batch *b, int16_t *d_pcm, size_t n_frames, double gain_db, int16_t *d_peaks)
+{
+    if (!b || !d_pcm || !d_peaks) return fail(TLB_E_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    // ref: src/odr-audioenc.cpp:1032: const double linear_gain_correction = pow(10.0, gain_dB / 20.0);
+    const double linear = std::pow(10.0, gain_db / 20.0);
+    mp2_launch_gain_peak(d_pcm, (long)n_frames, b->P.nch, linear, d_peaks, b->slot[0].stream);
+    b->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -195,3 +195,74 @@ def test_ensemble_of_services_in_one_call():
         c = oracle.configure(s["sample_rate"], s["mode"], s["bitrate"])
         want, _ = oracle.encode(c, s["pcm"])
         assert np.array_equal(got, want), (s["sample_rate"], s["mode"], s["bitrate"])
+
+
+def _gain_peak_model(pcm, nch, gain_db):
+    """numpy restatement of src/odr-audioenc.cpp:1020-1055 per frame: (left, right) pairs also in mono, truncated
+    product wrapped to 16 bits, peaks start at 0"""
+    flat = pcm.reshape(-1).astype(np.int64)
+    lin = 10.0 ** (gain_db / 20.0)
+    if lin != 1.0:
+        flat = np.trunc(flat * lin).astype(np.int64)
+        flat = ((flat + 32768) % 65536) - 32768
+    g = flat.astype(np.int16)
+    pairs = g.reshape(-1, nch * 1152 // 2, 2).astype(np.int64)
+    peaks = np.maximum(pairs.max(axis=1), 0).astype(np.int16)
+    return g.reshape(pcm.shape), peaks
+
+
+@pytest.mark.parametrize("cfg,gain_db", [("Bj", 0.0), ("Bj", -6.0), ("Bj", 3.5), ("C", 2.0), ("M48", -1.25)])
+def test_gain_and_peaks_on_device(cfg, gain_db):
+    """the step before the encoder (gain correction + peak levels) through tlb_batch_set_gain: peaks equal the model,
+    frames equal the oracle's encoding of the gained PCM, across chunk boundaries"""
+    import ctypes as C
+    import odr_audioenc_b200 as tl
+    n = 45
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, "S5" if gain_db > 0 else "S8", n)
+    nch = pcm.shape[1]
+    gained, want_peaks = _gain_peak_model(pcm, nch, gain_db)
+    e = _enc(fs, mode, br, chunk=8)
+    peaks = np.zeros((n, 2), dtype=np.int16)
+    L = tl.lib()
+    L.tlb_batch_set_gain.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    assert L.tlb_batch_set_gain(e._h, gain_db, peaks.ctypes.data) == 0
+    before = pcm.copy()
+    out = e.encode(pcm)
+    assert np.array_equal(pcm, before), "the caller's buffer must not be modified"
+    assert np.array_equal(peaks, want_peaks)
+    ref, _ = oracle.encode(oracle.configure(fs, mode, br), gained)
+    assert np.array_equal(out, ref)
+
+
+def test_example_cli_stream_and_batch_modes(tmp_path):
+    """examples/dabenc: WAV in, MP2 out.  Batch mode = the oracle's stream; --stream (the reference's per-frame API
+    and re-framing loop, src/odr-audioenc.cpp:1208-1225) = the same bytes minus what odr-audioenc leaves unwritten."""
+    import struct
+    import subprocess
+    import signals
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "dabenc")
+    n, fs, br = 60, 48000, 128
+    pcm = signals.make("S1", n, 2, fs)
+    wav = tmp_path / "in.wav"
+    data = pcm.tobytes()
+    with open(wav, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 2, fs, fs * 4, 4, 16)
+                + b"data" + struct.pack("<I", len(data)) + data)
+    ref, _ = oracle.encode(oracle.configure(fs, "j", br), pcm)
+    subprocess.run([exe, "-i", str(wav), "-o", str(tmp_path / "b.mp2"), "-b", str(br)], check=True)
+    assert np.array_equal(np.fromfile(tmp_path / "b.mp2", dtype=np.uint8), ref)
+    subprocess.run([exe, "-i", str(wav), "-o", str(tmp_path / "s.mp2"), "-b", str(br), "--stream"], check=True)
+    got = np.fromfile(tmp_path / "s.mp2", dtype=np.uint8)
+    lg = 3 * br
+    # the encoder's bit buffer keeps its newest bytes until it fills again and the re-framer holds one frame back
+    flushed = 0
+    held = 0
+    for _ in range(n):
+        held += lg
+        if held >= 4096:
+            flushed += 4096 - (lg + 4)
+            held -= 4096 - (lg + 4)
+    want_len = ((flushed - 1) // lg) * lg if flushed else 0
+    assert got.size == want_len and want_len > 0
+    assert np.array_equal(got, ref[:want_len])
