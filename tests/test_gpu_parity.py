@@ -266,3 +266,25 @@ def test_example_cli_stream_and_batch_modes(tmp_path):
     want_len = ((flushed - 1) // lg) * lg if flushed else 0
     assert got.size == want_len and want_len > 0
     assert np.array_equal(got, ref[:want_len])
+
+
+ODD = [(c, s) for c in ("L8", "J64", "M64", "L144", "H", "D", "L3", "T2") for s in ("S1", "S8")] + [("L8", "S3"), ("H", "S5")]
+
+
+@pytest.mark.parametrize("cfg,sig", ODD, ids=["%s-%s" % cs for cs in ODD])
+def test_corner_configurations(cfg, sig):
+    """the small and large ends of the rate tables: 8 kbit/s LSF mono (48-byte frames), 384 kbit/s, dual channel,
+    2-byte ScF-CRC rates, LSF stereo"""
+    n = 30
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    ref, _ = oracle.encode(oracle.configure(fs, mode, br), pcm)
+    assert np.array_equal(_enc(fs, mode, br, chunk=11).encode(pcm), ref)
+
+
+def test_degenerate_sizes():
+    fs, mode, br, pcm, _, _ = cases.make_case("Bj", "S1", 3)
+    e = _enc(fs, mode, br)
+    assert e.encode(pcm[:0], n_frames=0).size == 0
+    ref, _ = oracle.encode(oracle.configure(fs, mode, br), pcm)
+    assert np.array_equal(e.encode(pcm[:1152], n_frames=1), oracle.encode(oracle.configure(fs, mode, br), pcm[:1152])[0])
+    assert np.array_equal(e.encode(pcm), ref)

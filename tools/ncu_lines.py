@@ -20,7 +20,7 @@ top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 # several kernels may be in the report: take the first whose name matches
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern in r[1])
+start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and (kern + "(") in r[1])
 hdr = rows[start + 1]
 ci, cs, csrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 cti = hdr.index("Thread Instructions Executed")
@@ -36,7 +36,7 @@ with tempfile.TemporaryDirectory() as td:
     for cub in glob.glob(os.path.join(td, "*.cubin")):
         dis += subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
 sec = re.split(r"\n\s*\.section\s+\.text\.", dis)
-body = next(s for s in sec[1:] if kern in s.split("\n", 1)[0])
+body = next(s for s in sec[1:] if (kern + "E") in s.split("\n", 1)[0] or (kern + "I") in s.split("\n", 1)[0])
 lines, cur = [], 0
 for ln in body.split("\n"):
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
