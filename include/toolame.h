@@ -9,7 +9,7 @@
  *
  * Differences, all on error paths: an illegal bitrate makes toolame_set_bitrate return 1
  * (the reference exit()s inside BitrateIndex, common.c:110-115); psychoacoustic models other
- * than 1 are refused by toolame_set_psy_model; a missing CUDA device makes
+ * 3 is refused by toolame_set_psy_model; a missing CUDA device makes
  * toolame_encode_frame print an error and return 0.
  */
 #ifndef TOOLAME_B200_COMPAT_H
@@ -39,7 +39,7 @@ TLB_API int toolame_enable_byteswap(void);
 /* 's' stereo, 'd' dual channel, 'j' joint stereo, 'm' mono */
 TLB_API int toolame_set_channel_mode(const char mode);
 
-/* 0..3 are valid for the reference; this build implements model 1 */
+/* 0..3 are valid for the reference; this build implements models 0, 1 and 2 */
 TLB_API int toolame_set_psy_model(int new_model);
 
 /* kbit/s; must be called after toolame_set_samplerate and toolame_set_channel_mode (it depends on both) */

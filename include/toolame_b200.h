@@ -38,7 +38,7 @@ extern "C" {
 #define TLB_E_PARAM   (-1)  /* illegal sample rate / mode / bitrate / psy model / pad length */
 #define TLB_E_CUDA    (-2)  /* CUDA runtime error (tlb_last_error() has the text) */
 #define TLB_E_ARG     (-3)  /* NULL pointer, bad sizes, bad history */
-#define TLB_E_UNSUPP  (-4)  /* legal for the reference, not (yet) built here (psy models 0, 3; 44.1/22.05 kHz padding) */
+#define TLB_E_UNSUPP  (-4)  /* legal for the reference, not (yet) built here (psy model 3; 44.1/22.05 kHz padding) */
 
 /* Stream parameters: what the reference takes through toolame_set_samplerate / _set_channel_mode /
  * _set_bitrate / _set_psy_model / _set_pad (toolame.c:168-262). */
@@ -46,7 +46,7 @@ typedef struct {
     int32_t sample_rate;   /* Hz: 48000, 24000 (DAB); 32000 / 16000 also accepted */
     int32_t channel_mode;  /* 's', 'd', 'j' or 'm' */
     int32_t bitrate;       /* kbit/s, 0 = default of the reference (toolame.c:217-218) */
-    int32_t psy_model;     /* 1 (the odr-audioenc default) or 2 */
+    int32_t psy_model;     /* 0, 1 (the odr-audioenc default) or 2 */
     int32_t pad_len;       /* X-PAD + F-PAD bytes reserved per record, 0 = none (toolame_set_pad) */
 } tlb_config;
 

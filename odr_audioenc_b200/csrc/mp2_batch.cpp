@@ -58,7 +58,7 @@ int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
     default: return fail(TLB_E_PARAM, "illegal sample rate");
     }
     if (c.psy_model < 0 || c.psy_model > 3) return fail(TLB_E_PARAM, "illegal psy model"); // ref: toolame.c:204
-    if (c.psy_model != 1 && c.psy_model != 2) return fail(TLB_E_UNSUPP, "psychoacoustic models 1 and 2 are built");
+    if (c.psy_model == 3) return fail(TLB_E_UNSUPP, "psychoacoustic model 3 is not built (models 0, 1 and 2 are)");
     P.psy = c.psy_model;
     switch (c.channel_mode) { // ref: toolame.c:174-200
     case 's': P.mode = 0; P.mode_ext = 0; break;
@@ -259,6 +259,7 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
             while (j < P.sub_size && (MP2_LTG_LINE[fq][j] >> 4) == i) j++;
             T.mm_j1[i] = (uint8_t)j;
         }
+        mp2_psy0_init(T.ath_min, (double)cfg->sample_rate); // (FLOAT) s_freq[version][idx] * 1000: toolame.c:365
         if (cudaMalloc(&b->d_tables, sizeof T) != cudaSuccess ||
             cudaMemcpy(b->d_tables, &T, sizeof T, cudaMemcpyHostToDevice) != cudaSuccess) {
             tlb_batch_destroy(b);
@@ -491,8 +492,9 @@ const char *tlb_kernel_name(int k) { return k >= 0 && k < MP2_N_KERNELS ? MP2_KE
 const char *tlb_batch_kernel_name(const tlb_batch *b, int k)
 {
     static const char *const psy2_names[MP2_N_KERNELS] = {"k_filterbank", "k_spectrum2", "k_psy2", "", "k_alloc", "k_pack"};
+    static const char *const psy0_names[MP2_N_KERNELS] = {"k_filterbank", "k_psy0", "", "", "k_alloc", "k_pack"};
     if (k < 0 || k >= MP2_N_KERNELS) return "";
-    return b && b->P.psy == 2 ? psy2_names[k] : MP2_KERNEL_NAMES[k];
+    return b && b->P.psy == 2 ? psy2_names[k] : b && b->P.psy == 0 ? psy0_names[k] : MP2_KERNEL_NAMES[k];
 }
 
 int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops)

@@ -13,7 +13,7 @@ struct Mp2Params {
     int dab_ext, lg_frame, pad_len;
     int psy_freq, sub_size, cb_count;   // psy-1 table selectors (psycho_1.c:42-56)
     int bitrate_per_ch;                 // kbit/s per channel (psycho_1_threshold's ATH offset switch)
-    int psy;                            // psychoacoustic model: 1 or 2
+    int psy;                            // psychoacoustic model: 0, 1 or 2
 };
 
 // Per-stream lookup tables of the psychoacoustic model, built on the host at create time.
@@ -22,6 +22,7 @@ struct Mp2PsyTables {
     uint8_t band[512];   // FFT line -> critical band (critband.h boundaries); 255 outside every band
     uint8_t mm_j0[32];   // per subband: first threshold partition of psycho_1_minimum_mask's scan (255: past the end)
     uint8_t mm_j1[32];   // ... and one past its last partition
+    double ath_min[32];  // psy model 0: lowest absolute threshold per subband in dB (psycho_0.c:36-47)
 };
 
 // Start-up tables of psychoacoustic model 2 (host-computed: mp2_psy2_init.h), device copy.

@@ -96,3 +96,29 @@ static inline int mp2_psy2_init(mp2_psy2_tables *T, double sfreq)
     for (j = T->n_part + 1; j <= MP2_P2_CBANDS; j++) T->first_line[j] = MP2_P2_HBLK;
     return 0;
 }
+
+/* Psychoacoustic model 0 (ref: psycho_0.c:27-47, ath.c:7-49): lowest absolute threshold of hearing within each
+ * subband, in dB, evaluated on the host with libm as the reference does on its first call. */
+static inline double mp2_ath_db(double f)
+{   /* ref: ath.c:7-49 with value = 0 */
+    double ath;
+    if (f < -.3) f = 3410;
+    f /= 1000;
+    f = (0.01 > f) ? 0.01 : f;
+    f = (18.0 < f) ? 18.0 : f;
+    ath = 3.640 * pow(f, -0.8) - 6.800 * exp(-0.6 * pow(f - 3.4, 2.0)) + 6.000 * exp(-0.15 * pow(f - 8.7, 2.0)) +
+          (0.6 + 0.04 * 0.0) * 0.001 * pow(f, 4.0);
+    return ath + 0;
+}
+
+static inline void mp2_psy0_init(double ath_min[32], double sfreq)
+{
+    const double freqperline = sfreq / 1024.0;
+    int sb, i;
+    for (sb = 0; sb < 32; sb++) ath_min[sb] = 1000;
+    for (i = 0; i < 512; i++) {
+        const double thisfreq = i * freqperline;
+        const double ath_val = mp2_ath_db(thisfreq);
+        if (ath_val < ath_min[i >> 4]) ath_min[i >> 4] = ath_val;
+    }
+}

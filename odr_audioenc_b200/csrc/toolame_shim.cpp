@@ -99,8 +99,8 @@ int toolame_set_psy_model(int new_model)
         std::fprintf(stderr, "libtoolame-dab: Invalid PSY model %d\n", new_model);
         return 1;
     }
-    if (new_model != 1 && new_model != 2) {
-        std::fprintf(stderr, "libtoolame-b200: PSY model %d is not built (models 1 and 2 are)\n", new_model);
+    if (new_model == 3) {
+        std::fprintf(stderr, "libtoolame-b200: PSY model %d is not built (models 0, 1 and 2 are)\n", new_model);
         return 1;
     }
     g.psy = new_model;

@@ -740,7 +740,16 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
     }
     /* ref: toolame.c:361-452 (psy model switch); models 1 and 2 are restated */
     for (int ch = 0; ch < nch; ch++) {
-        if (c->psy == 2) mp2o_psy2_frame(c, pcm, ch, n, t->smr[ch]);
+        if (c->psy == 0) { /* ref: psycho_0.c:27-69: SMR from the smallest scalefactor index and the subband's lowest ATH */
+            static double ath_min[32], ath_for = 0;
+            if (ath_for != (double)c->fs_hz) { mp2_psy0_init(ath_min, (double)c->fs_hz); ath_for = (double)c->fs_hz; }
+            for (int sb = 0; sb < 32; sb++) {
+                int mn = t->scalar_pre[ch][0][sb];
+                for (int gr = 1; gr < 3; gr++)
+                    if (mn > t->scalar_pre[ch][gr][sb]) mn = t->scalar_pre[ch][gr][sb];
+                t->smr[ch][sb] = 2.0 * (30.0 - mn) - ath_min[sb];
+            }
+        } else if (c->psy == 2) mp2o_psy2_frame(c, pcm, ch, n, t->smr[ch]);
         else mp2o_psy1_frame(c, pcm, ch, n, t->scalar_pre[ch], t->smr[ch], t->ltmin[ch], t->spike[ch]);
     }
 
@@ -855,7 +864,7 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
 int mp2o_encode(const mp2o_cfg *c, const int16_t *pcm, long n_frames_total, long f0, long f1,
                 const uint8_t *xpad, uint8_t *out, mp2o_tap *taps)
 {
-    if (c->psy != 1 && c->psy != 2) return -1;
+    if (c->psy < 0 || c->psy > 2) return -1;
     static frame_out fo;
     for (long n = f0; n < f1 + 1 && n < n_frames_total; n++) {
         const uint8_t *rec = xpad ? xpad + (size_t)n * (c->pad_len + 1) : NULL;

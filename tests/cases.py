@@ -19,6 +19,9 @@ GOLDEN = [(c, s, 10) for c in ("A", "Bs", "Bj", "C", "M48", "T2", "T2j", "D", "E
 GOLDEN_PSY2 = [("E1", "S1", 10), ("E1", "S8", 10), ("E1", "S2", 10), ("Bj", "S8", 10), ("C", "S1", 10), ("T2j", "S8", 10),
                ("M48", "S6", 10), ("E1", "S7", 10)]
 
+# psychoacoustic model 0 (scalefactor + absolute-threshold heuristic, reachable with --dabpsy 0) -> tests/golden/psy0_*.npz
+GOLDEN_PSY0 = [("Bj", "S1", 10), ("Bj", "S8", 10), ("C", "S1", 10), ("T2j", "S8", 10), ("M48", "S6", 10), ("A", "S2", 10)]
+
 PAD_LEN = 23
 
 

@@ -288,3 +288,14 @@ def test_degenerate_sizes():
     ref, _ = oracle.encode(oracle.configure(fs, mode, br), pcm)
     assert np.array_equal(e.encode(pcm[:1152], n_frames=1), oracle.encode(oracle.configure(fs, mode, br), pcm[:1152])[0])
     assert np.array_equal(e.encode(pcm), ref)
+
+
+@pytest.mark.parametrize("cfg,sig,n", cases.GOLDEN_PSY0, ids=["%s-%s" % (c, s) for c, s, _ in cases.GOLDEN_PSY0])
+def test_psy0_bytes_equal_reference_golden(cfg, sig, n):
+    """psychoacoustic model 0 (--dabpsy 0): golden bytes of the reference, and a longer stream against the oracle"""
+    g = np.load(os.path.join(GOLD, "psy0_%s_%s.npz" % (cfg, sig)))
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    assert np.array_equal(_enc(fs, mode, br, psy=0).encode(pcm), g["bytes"])
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, 64)
+    ref, _ = oracle.encode(oracle.configure(fs, mode, br, 0), pcm)
+    assert np.array_equal(_enc(fs, mode, br, psy=0, chunk=13).encode(pcm), ref)

@@ -11,12 +11,12 @@ import oracle
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-ALL_GOLDEN = [(1,) + g for g in cases.GOLDEN] + [(2,) + g for g in cases.GOLDEN_PSY2]
+ALL_GOLDEN = [(1,) + g for g in cases.GOLDEN] + [(2,) + g for g in cases.GOLDEN_PSY2] + [(0,) + g for g in cases.GOLDEN_PSY0]
 
 
 @pytest.mark.parametrize("psy,cfg,sig,n", ALL_GOLDEN, ids=["psy%d-%s-%s" % (p, c, s) for p, c, s, _ in ALL_GOLDEN])
 def test_oracle_matches_golden(psy, cfg, sig, n):
-    g = np.load(os.path.join(GOLD, ("%s_%s.npz" if psy == 1 else "psy2_%s_%s.npz") % (cfg, sig)))
+    g = np.load(os.path.join(GOLD, ("%s_%s.npz" if psy == 1 else "psy%d_%%s_%%s.npz" % psy) % (cfg, sig)))
     fs, mode, br, pcm, pad_len, xpad = cases.make_case(cfg, sig, n)
     c = oracle.configure(fs, mode, br, psy, pad_len)
     out, tap = oracle.encode(c, pcm, xpad=xpad, taps=True)

@@ -49,3 +49,14 @@ def test_oracle_psy2_equals_reference(cfg, sig):
     r = reftool.run_ref(pcm, fs, mode, br, 2, taps=True)
     assert np.array_equal(out, r["bytes"])
     assert np.array_equal(tap["smr"][:, :c.nch], r["tap"]["smr"][:, :c.nch])
+
+
+@pytest.mark.parametrize("cfg,sig", [("Bj", "S8"), ("C", "S1"), ("A", "S4"), ("T2j", "S8"), ("M48", "S6"), ("H", "S2")])
+def test_oracle_psy0_equals_reference(cfg, sig):
+    n = 100
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    c = oracle.configure(fs, mode, br, 0)
+    out, tap = oracle.encode(c, pcm, taps=True)
+    r = reftool.run_ref(pcm, fs, mode, br, 0, taps=True)
+    assert np.array_equal(out, r["bytes"])
+    assert np.array_equal(tap["smr"][:, :c.nch], r["tap"]["smr"][:, :c.nch])

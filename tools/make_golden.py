@@ -16,12 +16,12 @@ import reftool  # noqa: E402
 
 out = os.path.join(ROOT, "tests", "golden")
 os.makedirs(out, exist_ok=True)
-for psy, cfg, sig, n in [(1,) + g for g in cases.GOLDEN] + [(2,) + g for g in cases.GOLDEN_PSY2]:
+for psy, cfg, sig, n in [(1,) + g for g in cases.GOLDEN] + [(2,) + g for g in cases.GOLDEN_PSY2] + [(0,) + g for g in cases.GOLDEN_PSY0]:
     fs, mode, br, pcm, pad_len, xpad = cases.make_case(cfg, sig, n)
     r = reftool.run_ref(pcm, fs, mode, br, psy, pad_len, xpad=xpad, taps=True, tapbig=True)
     t = r["tap"]
     np.savez_compressed(
-        os.path.join(out, ("%s_%s.npz" if psy == 1 else "psy2_%s_%s.npz") % (cfg, sig)), bytes=r["bytes"],
+        os.path.join(out, ("%s_%s.npz" if psy == 1 else "psy%d_%%s_%%s.npz" % psy) % (cfg, sig)), bytes=r["bytes"],
         pcm_crc=np.uint32(np.bitwise_xor.reduce(pcm.astype(np.uint16).ravel().astype(np.uint32) * np.arange(1, pcm.size + 1, dtype=np.uint32))),
         scalar=t["scalar"].astype(np.uint8), j_scale=t["j_scale"].astype(np.uint8), scfsi=t["scfsi"].astype(np.uint8),
         bit_alloc=t["bit_alloc"].astype(np.uint8), mode=t["mode"], mode_ext=t["mode_ext"], jsbound=t["jsbound"],
