@@ -57,6 +57,11 @@ def select_config(name):
 
 select_config("B")
 
+# dram__bytes_read.sum + dram__bytes_write.sum per frame of config B, from the ncu --set full capture summarised in
+# profiles/ncu_r1_summary.md (generation C, launches of 75 777 frames); bench.py scales it to its own launch size
+NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22943, "k_spectrum": 20498, "k_label": 17321, "k_threshold": 1973,
+                            "k_alloc": 625, "k_pack": 19443}
+
 
 def synth_pcm_torch(n_frames, seed, device):
     """S1-style signal of SURVEY.md 8(d) generated on the GPU in one-minute pieces (tones under a slow envelope,
@@ -471,7 +476,11 @@ def main():
     L.tlb_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tlb_fp64_peak(local, C.byref(dfma), C.byref(dmuladd))
     roofline = {"kernel": names[top], "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak,
+                "traffic": (NCU_DRAM_BYTES_PER_FRAME.get(names[top]) * frames_per_launch
+                            if args.config == "B" and names[top] in NCU_DRAM_BYTES_PER_FRAME else None),
+                "traffic_source": "ncu --set full, profiles/ncu_r1_summary.md (per frame x frames per launch)",
+                "algorithmic_bytes": kb * frames_per_launch, "peak_source": peak_src,
                 "fp64": {"achieved_tflops": kf * frames_per_launch / dur_s / 1e12, "peak_dmul_dadd_tflops": dmuladd.value,
                          "peak_dfma_tflops": dfma.value,
                          "frac_of_no_fma_peak": (kf * frames_per_launch / dur_s / 1e12) / dmuladd.value if dmuladd.value > 0 else None},
