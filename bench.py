@@ -84,6 +84,24 @@ def synth_pcm_torch(n_frames, seed, device):
     return out
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank (and allocate its pinned host buffers) on the CPUs next to its GPU: with several ranks per
+    node the host<->device copies otherwise cross the socket interconnect.  Best effort; returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -336,6 +354,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (this implementation has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -499,7 +518,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD + ", %.3g h synthetic PCM batch per GPU "
                                "(%d frames); inputs (%.2f GB) larger than L2" % (args.hours, n_frames, pcm_bytes / 1e9),
-                   "frames_per_gpu": n_frames, "x_realtime_per_gpu": value / world},
+                   "frames_per_gpu": n_frames, "x_realtime_per_gpu": value / world, "host_affinity_rank0": numa},
         "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "clocks": sampler.summary() if sampler else None,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
