@@ -79,8 +79,8 @@ TLB_API const char *tlb_last_error(void);
  *                     0: stream end, the last frame keeps its own ScF-CRC
  *   xpad              NULL, or n_frames+has_next records of pad_len+1 bytes in odr-audioenc's layout
  *                     (src/odr-audioenc.cpp:823-852): data right-aligned in the first pad_len bytes,
- *                     last byte = used length (0 or >= 2), i.e. what the caller passes to
- *                     toolame_encode_frame as xpad_data / xpad_len
+ *                     last byte = used length (0 or 2..pad_len; 1 is taken as 0 and larger values as
+ *                     pad_len), i.e. what the caller passes to toolame_encode_frame as xpad_data / xpad_len
  *   out               n_frames * lg_frame bytes
  * pcm / out may be pageable or pinned (tlb_host_alloc); pinned memory makes the copies asynchronous.
  */

@@ -31,7 +31,7 @@ def xpad_records(n_frames, pad_len=PAD_LEN, seed=99):
     import numpy as np
     rng = np.random.RandomState(seed)
     rec = rng.randint(0, 256, size=(n_frames, pad_len + 1)).astype(np.uint8)
-    used = rng.choice([0, 2, 3, 8, pad_len], size=n_frames)
+    used = rng.choice([u for u in (0, 2, 3, 8, pad_len) if u <= pad_len], size=n_frames)  # 0 or 2..pad_len
     rec[:, pad_len] = used
     return rec
 

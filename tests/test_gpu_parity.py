@@ -299,3 +299,62 @@ def test_psy0_bytes_equal_reference_golden(cfg, sig, n):
     fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, 64)
     ref, _ = oracle.encode(oracle.configure(fs, mode, br, 0), pcm)
     assert np.array_equal(_enc(fs, mode, br, psy=0, chunk=13).encode(pcm), ref)
+
+
+def test_randomised_configurations_and_ranges():
+    """seeded random walk over the legal parameter space: sample rate, mode, bitrate, psy model, X-PAD, launch chunk
+    size, signal statistics (level, DC, clipping, sparse impulses) and the encoded range; bytes equal the oracle"""
+    rng = np.random.RandomState(20260)
+    rates = {48000: [32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384],
+             24000: [8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160]}
+    done = 0
+    for _ in range(60):
+        fs = int(rng.choice([48000, 24000]))
+        mode = str(rng.choice(["s", "j", "d", "m"]))
+        br = int(rng.choice(rates[fs]))
+        if fs == 48000 and mode != "m" and br < 64:
+            continue  # per-channel rate below the smallest MPEG-1 allocation table's range: illegal in ISO 11172-3
+        if fs == 48000 and mode == "m" and br > 192:
+            continue
+        psy = int(rng.choice([0, 1, 1, 2]))
+        pad_len = int(rng.choice([0, 0, 6, 23, 58]))
+        n = int(rng.randint(3, 16))
+        nch = 1 if mode == "m" else 2
+        kind = rng.randint(4)
+        if kind == 0:
+            pcm = rng.randint(-32768, 32768, size=(n * 1152, nch)).astype(np.int16)
+        elif kind == 1:
+            pcm = (rng.randn(n * 1152, nch) * rng.choice([3, 300, 9000])).clip(-32768, 32767).astype(np.int16)
+        elif kind == 2:
+            t = np.arange(n * 1152)[:, None]
+            pcm = (12000 * np.sin(t * rng.uniform(0.001, 1.5, size=(1, nch))) + rng.randint(-4000, 4000)).astype(np.int16)
+        else:
+            pcm = np.zeros((n * 1152, nch), dtype=np.int16)
+            pcm[rng.randint(0, n * 1152, size=5)] = rng.randint(-32768, 32768, size=(5, nch))
+        xpad = None
+        if pad_len:
+            xpad = cases.xpad_records(n, pad_len, seed=int(rng.randint(1 << 30)))
+            if br * (3 if fs == 48000 else 6) < pad_len + 60:
+                continue
+        try:
+            c = oracle.configure(fs, mode, br, psy, pad_len)
+        except ValueError:
+            continue
+        ref, _ = oracle.encode(c, pcm, xpad=xpad)
+        halo = 1632 if psy == 2 else 480
+        e = _enc(fs, mode, br, pad_len, chunk=int(rng.randint(1, 9)), psy=psy)
+        f0 = int(rng.randint(0, n))
+        f1 = int(rng.randint(f0 + 1, n + 1))
+        hist = f0 * 1152 if f0 * 1152 < halo else int(rng.randint(halo, f0 * 1152 + 1))
+        if f0 and hist < halo:
+            hist, f0 = 0, 0
+        has_next = f1 < n
+        seg = pcm[f0 * 1152 - hist:(f1 + has_next) * 1152]
+        got = e.encode(seg, history=hist, has_next=has_next, xpad=None if xpad is None else xpad[f0:f1 + has_next])
+        want = ref[f0 * c.lg_frame:f1 * c.lg_frame]
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, "cfg %s: %d bytes differ, first at frame %d byte %d of %d" % (
+            (fs, mode, br, psy, pad_len, n, f0, f1, hist, kind), bad.size, bad[0] // c.lg_frame if bad.size else -1,
+            bad[0] % c.lg_frame if bad.size else -1, c.lg_frame)
+        done += 1
+    assert done >= 30
