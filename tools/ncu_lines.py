@@ -20,7 +20,7 @@ top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 # several kernels may be in the report: take the first whose name matches
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and (kern + "(") in r[1])
+start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and ((kern + "(") in r[1] or (kern + "<") in r[1]))
 hdr = rows[start + 1]
 ci, cs, csrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 cti = hdr.index("Thread Instructions Executed")
