@@ -114,7 +114,7 @@ struct Slot {
     double *smr = nullptr, *psy_x = nullptr, *psy_w = nullptr, *spike = nullptr;
     unsigned *psy_cand = nullptr, *psy_t0 = nullptr;
     Mp2Maskers *maskers = nullptr;
-    double *p2_energy = nullptr, *p2_phi = nullptr;
+    double *p2_energy = nullptr, *p2_phi = nullptr, *p2_r = nullptr;
     int16_t *d_peaks = nullptr; // [fa + 1][2]
     tlb_side *side = nullptr;
     cudaStream_t stream = nullptr;
@@ -169,6 +169,7 @@ int alloc_slot(tlb_batch *b, Slot &s)
     if (b->P.psy == 2) {
         CU(cudaMalloc(&s.p2_energy, (2 * fa + 2) * nch * 520 * sizeof(double)));
         CU(cudaMalloc(&s.p2_phi, (2 * fa + 2) * nch * 520 * sizeof(double)));
+        CU(cudaMalloc(&s.p2_r, (2 * fa + 2) * nch * 520 * sizeof(double)));
     } else {
         CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
         CU(cudaMalloc(&s.psy_w, tiles * 512 * 32 * sizeof(double)));
@@ -189,7 +190,7 @@ void free_slot(Slot &s)
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
     cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
-    cudaFree(s.p2_energy); cudaFree(s.p2_phi); cudaFree(s.d_peaks);
+    cudaFree(s.p2_energy); cudaFree(s.p2_phi); cudaFree(s.p2_r); cudaFree(s.d_peaks);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s = Slot();
@@ -202,7 +203,7 @@ Mp2Chunk chunk_of(const tlb_batch *b, const Slot &s, const int16_t *pcm, long lo
     Mp2Chunk c;
     c.pcm = pcm; c.lo = lo; c.xpad = xpad; c.sb = s.sb; c.scalar_pre = s.scalar_pre; c.j_scale = s.j_scale;
     c.smr = s.smr; c.side = s.side; c.psy_x = s.psy_x; c.psy_w = s.psy_w; c.psy_cand = s.psy_cand; c.psy_t0 = s.psy_t0;
-    c.spike = s.spike; c.maskers = s.maskers; c.p2_energy = s.p2_energy; c.p2_phi = s.p2_phi;
+    c.spike = s.spike; c.maskers = s.maskers; c.p2_energy = s.p2_energy; c.p2_phi = s.p2_phi; c.p2_r = s.p2_r;
     c.p2_first_block = lo == 0 ? 0 : -2; // at the stream start the blocks before the first frame are the zero state
     c.out = out; c.fa = fa; c.n_out = n_out;
     return c;
