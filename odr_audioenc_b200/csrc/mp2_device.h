@@ -37,9 +37,9 @@ struct Mp2Psy2Tables {
 
 // Surviving maskers of one (frame, channel), in the order psycho_1_threshold visits them.
 struct Mp2Maskers {
-    double t_x[96];       // tonal: level in dB
+    double t_x[104];      // tonal: level in dB
     double n_x[28];       // noise
-    uint8_t t_part[96];   // threshold-table partition of the masker's line (index into the bark table)
+    uint8_t t_part[104];  // threshold-table partition of the masker's line (index into the bark table)
     uint8_t n_part[28];
     int n_tone, n_noise;
 };

@@ -358,3 +358,20 @@ def test_randomised_configurations_and_ranges():
             bad[0] % c.lg_frame if bad.size else -1, c.lg_frame)
         done += 1
     assert done >= 30
+
+
+@pytest.mark.parametrize("sig,f0,f1", [("S1", 1198, 1208), ("S8", 3090, 3099), ("S2", 928, 936), ("S1", 16860, 16870)])
+def test_frames_where_tonal_and_noise_lists_merge(sig, f0, f1):
+    """frames found by the parity sweep: the first tonal is wiped by the second and a noise masker lands on its line, so
+    the reference's tonal list continues into the noise list (those maskers count twice in the threshold)"""
+    import signals
+    import odr_audioenc_b200 as tl
+    n = f1 + 1
+    pcm = signals.make(sig, n, 2, 48000)
+    c = oracle.configure(48000, "j", 192)
+    ref, tap = oracle.encode(c, pcm, f0, f1, taps=True)
+    e = _enc(48000, "j", 192)
+    got = e.encode(pcm[(f0 - 1) * 1152:], n_frames=f1 - f0, history=1152, has_next=True)
+    smr = e.tap(tl.TAP_SMR, f1 - f0)[:, :, :c.sblimit]
+    assert np.abs(smr - tap["smr"][:, :, :c.sblimit]).max() < 1e-9
+    assert np.array_equal(got, ref)
