@@ -58,9 +58,9 @@ def select_config(name):
 select_config("B")
 
 # dram__bytes_read.sum + dram__bytes_write.sum per frame of config B, from the ncu --set full capture summarised in
-# profiles/ncu_r1_summary.md (generation C, launches of 75 777 frames); bench.py scales it to its own launch size
-NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22943, "k_spectrum": 20498, "k_label": 17321, "k_threshold": 1973,
-                            "k_alloc": 625, "k_pack": 19443}
+# profiles/ncu_r1_summary.md (end of round, launches of 75 777 frames); bench.py scales it to its own launch size
+NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22804, "k_spectrum": 20482, "k_label": 29852, "k_threshold": 2002,
+                            "k_alloc": 625, "k_pack": 19437}
 
 
 def synth_pcm_torch(n_frames, seed, device):
