@@ -375,3 +375,15 @@ def test_frames_where_tonal_and_noise_lists_merge(sig, f0, f1):
     smr = e.tap(tl.TAP_SMR, f1 - f0)[:, :, :c.sblimit]
     assert np.abs(smr - tap["smr"][:, :, :c.sblimit]).max() < 1e-9
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("cfg,sig,psy", [("Bj", "S8", 1), ("C", "S1", 1), ("T2j", "S2", 1), ("E1", "S8", 2), ("D", "S6", 0)])
+def test_gpu_streams_pass_the_independent_structural_checker(cfg, sig, psy):
+    """sync words, header fields, CRC-16 over the protected bits, frame pitch, audio data within the frame, DAB
+    ScF-CRC of the following frame: verified by a parser that shares nothing with the oracle (tests/mp2_check.py)"""
+    import mp2_check
+    n = 25
+    fs, mode, br, pcm, _, _ = cases.make_case(cfg, sig, n)
+    out = _enc(fs, mode, br, psy=psy, chunk=9).encode(pcm)
+    frames = mp2_check.check_stream(out)
+    assert len(frames) == n and frames[0]["kbps"] == br and frames[0]["fs"] == fs
