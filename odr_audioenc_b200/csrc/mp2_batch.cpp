@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -269,8 +270,11 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
         }
     }
     if (P.psy == 2) {
-        static mp2_psy2_tables H; // host-side start-up tables, evaluated with libm as the reference does
-        static Mp2Psy2Tables D;
+        // host-side start-up tables, evaluated with libm as the reference does (heap: 33 kB each, and re-entrant)
+        std::unique_ptr<mp2_psy2_tables> Hp(new mp2_psy2_tables);
+        std::unique_ptr<Mp2Psy2Tables> Dp(new Mp2Psy2Tables);
+        mp2_psy2_tables &H = *Hp;
+        Mp2Psy2Tables &D = *Dp;
         if (mp2_psy2_init(&H, (double)cfg->sample_rate)) { tlb_batch_destroy(b); return fail(TLB_E_PARAM, "psy-2 tables"); }
         std::memset(&D, 0, sizeof D);
         for (int j = 0; j < 64; j++)
