@@ -28,16 +28,34 @@ SEG = 500  # frames per oracle work item
 
 
 def _oracle_seg(job):
-    cfg_name, sig, n, f0, f1 = job
+    cfg_name, sig, n, f0, f1, pcm_path = job
     fs, mode, br = cases.CONFIGS[cfg_name]
     nch = 1 if mode == "m" else 2
-    pcm = signals.make(sig, n, nch, fs)
+    pcm = np.memmap(pcm_path, dtype=np.int16, mode="r").reshape(-1, nch)  # written once by the parent
     c = oracle.configure(fs, mode, br, PSY)
     out, tap = oracle.encode(c, pcm, f0, f1, taps=True)
     return f0, out, tap["smr"].copy(), tap["bit_alloc"].copy(), tap["scalar"].copy()
 
 
+def make_long(sig, n, nch, fs, piece=20000):
+    """signals.make in pieces of `piece` frames (bounded memory); the pieces continue the same seeded signal where
+    its definition is a function of absolute time / sample index, so up to `piece` frames it equals signals.make"""
+    if n <= piece:
+        return signals.make(sig, n, nch, fs)
+    out = np.empty((n * 1152, nch), dtype=np.int16)
+    for k, f0 in enumerate(range(0, n, piece)):
+        m = min(piece, n - f0)
+        if sig in ("S1", "S8", "S2"):
+            out[f0 * 1152:(f0 + m) * 1152] = signals.SIGNALS[sig](m * 1152, nch, fs, seed={"S1": 12345, "S8": 777, "S2": 1}[sig] + 7919 * k)
+        else:
+            out[f0 * 1152:(f0 + m) * 1152] = signals.make(sig, m, nch, fs)
+    return out
+
+
 def main():
+    import tempfile
+    os.environ["TLB_HOST_CHUNK"] = str(1 << 30)  # one launch chunk per case, so that the taps cover every frame
+    tmp_dir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
     out_path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "parity_sweep.json")
     import odr_audioenc_b200 as tl
@@ -47,12 +65,14 @@ def main():
             fs, mode, br = cases.CONFIGS[cfg_name]
             nch = 1 if mode == "m" else 2
             t0 = time.time()
-            pcm = signals.make(sig, n, nch, fs)
+            pcm = make_long(sig, n, nch, fs)
+            pcm_path = os.path.join(tmp_dir, "pcm.bin")
+            pcm.tofile(pcm_path)
             enc = tl.BatchEncoder(fs, mode, br, PSY, chunk_frames=n + 1)
             got = enc.encode(pcm).reshape(n, -1)
             smr = enc.tap(tl.TAP_SMR, n)
             side = enc.tap(tl.TAP_SIDE, n)
-            jobs = [(cfg_name, sig, n, f0, min(f0 + SEG, n)) for f0 in range(0, n, SEG)]
+            jobs = [(cfg_name, sig, n, f0, min(f0 + SEG, n), pcm_path) for f0 in range(0, n, SEG)]
             bad_frames, smr_off, first_stage = [], 0, {"scalefactor": 0, "bit_alloc": 0, "bytes_only": 0}
             for f0, want, o_smr, o_alloc, o_scalar in pool.imap_unordered(_oracle_seg, jobs):
                 k = want.size // got.shape[1]
@@ -79,6 +99,8 @@ def main():
     print("TOTAL %d frames, %d differ -> %.5f %% identical" % (tot, tot_bad, 100 * (1 - tot_bad / tot)))
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     json.dump(summary, open(out_path, "w"), indent=1)
+    import shutil
+    shutil.rmtree(tmp_dir, ignore_errors=True)
 
 
 if __name__ == "__main__":
