@@ -387,3 +387,25 @@ def test_gpu_streams_pass_the_independent_structural_checker(cfg, sig, psy):
     out = _enc(fs, mode, br, psy=psy, chunk=9).encode(pcm)
     frames = mp2_check.check_stream(out)
     assert len(frames) == n and frames[0]["kbps"] == br and frames[0]["fs"] == fs
+
+
+def test_argument_errors_are_reported_not_fatal():
+    import ctypes as C
+    import odr_audioenc_b200 as tl
+    e = _enc(48000, "j", 192)
+    pcm = np.zeros((4 * 1152, 2), dtype=np.int16)
+    with pytest.raises(tl.TlbError, match="history"):
+        e.encode(pcm, n_frames=2, history=100)  # a history shorter than the 480-sample halo is refused
+    L = tl.lib()
+    out = np.zeros(2 * e.lg_frame, dtype=np.uint8)
+    assert L.tlb_batch_encode(e._h, None, 2, 0, 0, None, out.ctypes.data) == -3  # TLB_E_ARG
+    assert L.tlb_batch_encode(None, pcm.ctypes.data, 2, 0, 0, None, out.ctypes.data) == -3
+    assert b"NULL" in L.tlb_last_error()
+    e2 = _enc(48000, "j", 256, psy=2)
+    with pytest.raises(tl.TlbError, match="history"):
+        e2.encode(pcm, n_frames=2, history=1152)  # psy model 2 needs 1632 samples
+    assert np.array_equal(e.encode(pcm), oracle.encode(oracle.configure(48000, "j", 192), pcm)[0])  # still usable
+    # the drop-in setters keep the reference's return convention (toolame.c:168-262)
+    assert L.toolame_init() == 0 and L.toolame_set_samplerate(44000) == -1 and L.toolame_set_channel_mode(b"x") == 1
+    assert L.toolame_set_psy_model(7) == 1 and L.toolame_set_pad(-1) == 1 and L.toolame_set_samplerate(48000) == 0
+    assert L.toolame_set_channel_mode(b"j") == 0 and L.toolame_set_bitrate(100) == 1 and L.toolame_set_bitrate(192) == 0
