@@ -446,7 +446,7 @@ def main():
         def step_host():
             enc.encode(h_pcm, n_frames=n_frames, out=h_out)
 
-        _, wall = timed(step_host, args.steps, 1, sync_each=True)
+        _, wall = timed(step_host, args.steps, args.warmup, sync_each=True)
         wall = allmax(wall)
         e2e = {"value": audio_s_total * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes * world,
                "d2h_bytes_per_step": out_bytes * world}
