@@ -373,7 +373,6 @@ def main():
     d_pcm = synth_pcm_torch(n_frames, 1000 + rank, dev)
     d_out = torch.empty(n_frames * lg, dtype=torch.uint8, device=dev)
     pcm_bytes, out_bytes = d_pcm.numel() * 2, d_out.numel()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB); inputs (6.9 GB) exceed L2 anyway
 
     def step_device():
         enc.encode_device(d_pcm.data_ptr(), n_frames, 0, False, None, d_out.data_ptr())
@@ -524,7 +523,6 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "parity_check": {"frames": chk_n, "byte_identical_to_oracle": parity_frames_equal},
     }
-    del flush
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
