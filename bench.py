@@ -493,6 +493,14 @@ def main():
     dfma, dmuladd = C.c_double(), C.c_double()
     L.tlb_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tlb_fp64_peak(local, C.byref(dfma), C.byref(dmuladd))
+    for name, rec in per_kernel.items():  # every kernel against both rooflines (algorithmic bytes / flops per launch)
+        kb_k, kf_k = KERNEL_ALG.get(name, (0, 0))
+        if rec["launches"] and rec["avg_ms"] > 0:
+            fpl = n_frames * (prof_steps + 1) / rec["launches"]
+            rec["hbm_gbs"] = kb_k * fpl / (rec["avg_ms"] * 1e-3) / 1e9
+            rec["hbm_frac"] = rec["hbm_gbs"] / hbm_peak
+            rec["fp64_tflops"] = kf_k * fpl / (rec["avg_ms"] * 1e-3) / 1e12
+            rec["fp64_frac_of_no_fma_peak"] = rec["fp64_tflops"] / dmuladd.value if dmuladd.value > 0 else None
     roofline = {"kernel": names[top], "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak,
                 "traffic": (NCU_DRAM_BYTES_PER_FRAME.get(names[top]) * frames_per_launch
