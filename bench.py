@@ -510,7 +510,8 @@ def main():
                 "fp64": {"achieved_tflops": kf * frames_per_launch / dur_s / 1e12, "peak_dmul_dadd_tflops": dmuladd.value,
                          "peak_dfma_tflops": dfma.value,
                          "frac_of_no_fma_peak": (kf * frames_per_launch / dur_s / 1e12) / dmuladd.value if dmuladd.value > 0 else None},
-                "kernels": per_kernel, "serialised_ms_per_step": serial_s / prof_steps * 1e3}
+                "kernels": per_kernel, "serialised_ms_per_step": serial_s / prof_steps * 1e3,
+                "frames_per_launch": frames_per_launch}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -44,7 +44,9 @@ constexpr int HALO = 1664;        // samples of history staged per chunk: the fi
 constexpr int HALO_PSY1 = 480, HALO_PSY2 = 1632;
 constexpr size_t DEFAULT_CHUNK = 148 * 512; // frames per launch: a multiple of the SM count, large enough to fill the
                                             // thread-per-frame kernels (k_label, k_alloc) with warps
-constexpr size_t HOST_CHUNK = 148 * 256;    // host-buffer path: smaller pieces so copies overlap the kernels
+constexpr size_t HOST_CHUNK = 148 * 128;    // host-buffer path: smaller pieces, three in flight, so that the H2D engine
+                                            // never waits (measured end to end: 2 x 37888: 264k, 3 x 37888: 272k,
+                                            // 3 x 18944: 280k, 4 x 18944: 279k x real time; the copy alone allows 282k)
 
 int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
 {
@@ -131,7 +133,9 @@ struct tlb_batch {
     tlb_info info;
     int device = 0;
     size_t chunk = 0;
-    static constexpr int NSLOT = 2; // in-flight chunks (measured: 1 lane 323k, 2 lanes 346k, 3 lanes 342k x real time)
+    static constexpr int NSLOT = 3; // in-flight chunks: the host-buffer path rotates over all three (copies of one
+                                    // chunk overlap kernels of the others), the device-resident path uses two
+                                    // (measured: 1 lane 323k, 2 lanes 346k, 3 lanes 342k x real time)
     Slot slot[NSLOT];
     Mp2PsyTables *d_tables = nullptr;
     Mp2Psy2Tables *d_tables2 = nullptr;
@@ -335,13 +339,15 @@ int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, si
     const size_t nch = (size_t)b->P.nch, lg = (size_t)b->P.lg_frame, rec = (size_t)b->P.pad_len + 1;
     const bool use_xpad = xpad && b->P.pad_len;
     size_t k = 0;
+    size_t host_lanes = tlb_batch::NSLOT;
+    if (const char *e = std::getenv("TLB_HOST_LANES")) host_lanes = (size_t)std::max(1, std::min((int)tlb_batch::NSLOT, std::atoi(e)));
     size_t chunk = std::min(b->chunk, HOST_CHUNK);
     if (const char *e = std::getenv("TLB_HOST_CHUNK")) { // tuning knob: frames per host<->device pipeline stage
         const long v = std::atol(e);
         if (v > 0) chunk = std::min(b->chunk, (size_t)v);
     }
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
-        Slot &s = b->slot[k & 1];
+        Slot &s = b->slot[k % host_lanes];
         const size_t n_out = std::min(chunk, n_frames - f0);
         const bool next_here = f0 + n_out < n_frames || has_next;
         const size_t fa = n_out + (next_here ? 1 : 0);
@@ -364,7 +370,7 @@ int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, si
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + f0 * lg, s.d_out, n_out * lg, cudaMemcpyDeviceToHost, s.stream));
         s.last_fa = (int)fa;
-        b->last_slot = (int)(k & 1);
+        b->last_slot = (int)(k % host_lanes);
     }
     return 0;
 }
@@ -419,7 +425,7 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
     // (several kernels are latency-bound on their own).  Towards the caller the call behaves as if it ran on slot
     // 0's stream: the other streams fork from it here and join it at the end.
     const size_t n_chunks = (n_frames + b->chunk - 1) / b->chunk;
-    int lanes = b->profile ? 1 : (int)std::min<size_t>(n_chunks, tlb_batch::NSLOT); // per-kernel timing: one at a time
+    int lanes = b->profile ? 1 : (int)std::min<size_t>(n_chunks, 2); // per-kernel timing: one at a time
     if (const char *e = std::getenv("TLB_DEVICE_LANES")) lanes = std::max(1, std::min(lanes, std::atoi(e)));
     for (int i = 1; i < lanes; i++) {
         CU(cudaEventRecord(b->slot[0].done, b->slot[0].stream));
