@@ -462,10 +462,11 @@ def main():
     # ---- parity spot check against the oracle (the checker, never the thing measured)
     import oracle
     chk_f0, chk_n = n_frames // 2, 64
-    seg = d_pcm[(chk_f0 * 1152 - 1152):(chk_f0 + chk_n + 1) * 1152].cpu().numpy()
+    lead = 2  # leading frames: the oracle starts its history at the segment start; frames `lead`.. then see their true
+    #           halo (480 samples for the filterbank and psy model 1, 1632 = two blocks back for psy model 2)
+    seg = d_pcm[(chk_f0 - lead) * 1152:(chk_f0 + chk_n + 1) * 1152].cpu().numpy()
     ocfg = oracle.configure(FS, MODE, KBPS, PSY)
-    want, _ = oracle.encode(ocfg, np.concatenate([np.zeros((0, NCH), np.int16), seg]), 1, 1 + chk_n)
-    # (the oracle starts its history at the segment start; one leading frame gives frames 1.. their true 480-sample halo)
+    want, _ = oracle.encode(ocfg, seg, lead, lead + chk_n)
     got = d_out[chk_f0 * lg:(chk_f0 + chk_n) * lg].cpu().numpy()
     parity_frames_equal = int((got.reshape(chk_n, -1) == want.reshape(chk_n, -1)).all(axis=1).sum())
 
