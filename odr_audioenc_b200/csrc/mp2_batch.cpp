@@ -426,7 +426,8 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
     // 0's stream: the other streams fork from it here and join it at the end.
     const size_t n_chunks = (n_frames + b->chunk - 1) / b->chunk;
     int lanes = b->profile ? 1 : (int)std::min<size_t>(n_chunks, 2); // per-kernel timing: one at a time
-    if (const char *e = std::getenv("TLB_DEVICE_LANES")) lanes = std::max(1, std::min(lanes, std::atoi(e)));
+    if (const char *e = std::getenv("TLB_DEVICE_LANES")) // tuning knob
+        lanes = b->profile ? 1 : std::max(1, std::min((int)std::min<size_t>(n_chunks, tlb_batch::NSLOT), std::atoi(e)));
     for (int i = 1; i < lanes; i++) {
         CU(cudaEventRecord(b->slot[0].done, b->slot[0].stream));
         CU(cudaStreamWaitEvent(b->slot[i].stream, b->slot[0].done, 0));
