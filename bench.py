@@ -59,8 +59,8 @@ select_config("B")
 
 # dram__bytes_read.sum + dram__bytes_write.sum per frame of config B, from the ncu --set full capture summarised in
 # profiles/ncu_r1_summary.md (end of round, launches of 75 777 frames); bench.py scales it to its own launch size
-NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22804, "k_spectrum": 20482, "k_label": 29852, "k_threshold": 2002,
-                            "k_alloc": 625, "k_pack": 19437}
+NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22774, "k_spectrum": 20479, "k_label": 30285, "k_threshold": 1966,
+                            "k_alloc": 623, "k_pack": 19667}
 
 
 def synth_pcm_torch(n_frames, seed, device):
