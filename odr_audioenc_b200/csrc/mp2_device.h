@@ -52,7 +52,7 @@ struct Mp2Chunk {
     double *sb;             // [fa][nch][36][32]
     uint8_t *scalar_pre;    // [fa][2][3][32]
     uint8_t *j_scale;       // [fa][3][32]
-    double *psy_x;          // [ceil(fa*nch/32)][512][32]  dB spectrum, tile layout (see mp2_kernels.cu)
+    double *psy_x;          // [ceil(fa*nch/32)][64 chunks][32 items][8 lines]  dB spectrum (psy_line() in mp2_kernels.cu)
     double *psy_w;          // same layout: noise-centre weight of each line
     unsigned *psy_cand;     // [fa*nch][16] tonal-candidate mask
     unsigned *psy_t0;       // [fa*nch][16] candidates passing the neighbourhood test on the unmodified spectrum
