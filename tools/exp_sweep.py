@@ -1,6 +1,9 @@
 #!/usr/bin/env python3
-"""Run bench.py (device-resident leg only) over (TLB_EXP, chunk size) pairs and print per-kernel ns per frame.
-usage: exp_sweep.py EXP:CHUNK [EXP:CHUNK ...]   (run on the GPU box; results appended to gpurun_out/exp_sweep.jsonl)"""
+"""A/B harness: run bench.py (device-resident leg only) over (TLB_EXP, chunk size[, extra bench.py flags]) triples and
+print per-kernel ns per frame (serialised) and the whole step overlapped.  TLB_EXP is an integer handed to the library
+through the environment; it only means something while mp2_launch_chunk has experiment switches compiled in (the
+variants measured in round 1 are listed in profiles/ncu_r1_summary.md; the losers were removed from the source).
+usage: exp_sweep.py EXP:CHUNK[:--flag=..] [...]   (run on the GPU box; results appended to gpurun_out/exp_sweep.jsonl)"""
 import json
 import os
 import subprocess
