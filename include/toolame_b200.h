@@ -60,8 +60,9 @@ typedef struct {
 typedef struct tlb_batch tlb_batch;
 
 /* Create an encoder for one stream configuration on CUDA device `device`.
- * max_chunk_frames = frames per kernel launch (0 = default); device working memory is
- * about 20 kB per chunk frame and per in-flight chunk (two chunks are in flight). */
+ * max_chunk_frames = frames per kernel launch (0 = default: 75 776); device working memory is
+ * about 40 kB per chunk frame (stereo, psy model 1) for each of the three chunk slots the encoder keeps
+ * (two in flight on the device-resident path, three smaller ones on the host-buffer path). */
 TLB_API int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames);
 TLB_API void tlb_batch_destroy(tlb_batch *b);
 TLB_API int tlb_batch_info(const tlb_batch *b, tlb_info *info);
