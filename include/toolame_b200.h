@@ -57,12 +57,17 @@ typedef struct {
     int32_t halo_samples;       /* PCM history a frame needs before its first sample (480; 1632 with psy model 2) */
 } tlb_info;
 
+/* Validate a configuration and derive its constants on the host -- no CUDA call, usable without a GPU (what
+ * toolame_set_bitrate needs: toolame.c:212-237 / BitrateIndex common.c:95-116).  info may be NULL. */
+TLB_API int tlb_config_check(const tlb_config *cfg, tlb_info *info);
+
 typedef struct tlb_batch tlb_batch;
 
 /* Create an encoder for one stream configuration on CUDA device `device`.
  * max_chunk_frames = frames per kernel launch (0 = default: 75 776); device working memory is
- * about 40 kB per chunk frame (stereo, psy model 1) for each of the three chunk slots the encoder keeps
- * (two in flight on the device-resident path, three smaller ones on the host-buffer path). */
+ * about 40 kB per chunk frame (stereo, psy model 1) for each chunk slot in use.  Slots are allocated on first use
+ * and sized for the path that uses them: two of max_chunk_frames on the device-resident path, three of
+ * min(max_chunk_frames, 18 944) on the host-buffer path (never more than the call's n_frames). */
 TLB_API int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames);
 TLB_API void tlb_batch_destroy(tlb_batch *b);
 TLB_API int tlb_batch_info(const tlb_batch *b, tlb_info *info);

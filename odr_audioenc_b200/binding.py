@@ -64,6 +64,7 @@ def lib():
         L.toolame_set_samplerate.argtypes = [C.c_long]
         L.toolame_encode_frame.argtypes = [vp, vp, sz, vp, sz]
         L.toolame_finish.argtypes = [vp, sz]
+        L.tlb_config_check.argtypes = [C.POINTER(_Config), C.POINTER(_Info)]
         _lib = L
     return _lib
 

@@ -123,6 +123,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     int last_fa = 0;
+    size_t cap = 0;             // frames (incl. the look-ahead frame) the buffers above are sized for; 0 = not allocated
 };
 
 } // namespace
@@ -159,12 +160,20 @@ const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS] = {"k_filterbank", "k_spectrum
 
 namespace {
 
-int alloc_slot(tlb_batch *b, Slot &s)
+void free_buffers(Slot &s);
+
+// Working memory of one in-flight chunk, sized for `frames` output frames (+ the look-ahead frame).  Slots are
+// allocated on first use and for the chunk size of the path that uses them: the host-buffer path stages
+// min(chunk, HOST_CHUNK) frames per slot, the device-resident path whole chunks on two of the three slots.
+int alloc_slot(tlb_batch *b, Slot &s, size_t frames)
 {
-    const size_t fa = b->chunk + 1, nch = (size_t)b->P.nch;
+    if (s.cap >= frames + 1) return 0;
+    if (s.stream) CU(cudaStreamSynchronize(s.stream)); // growing: nothing may still be using the old buffers
+    free_buffers(s);
+    const size_t fa = frames + 1, nch = (size_t)b->P.nch;
     CU(cudaMalloc(&s.d_pcm, (HALO + fa * 1152) * nch * sizeof(int16_t)));
     CU(cudaMalloc(&s.d_xpad, fa * (size_t)(b->P.pad_len + 1)));
-    CU(cudaMalloc(&s.d_out, b->chunk * (size_t)b->P.lg_frame));
+    CU(cudaMalloc(&s.d_out, frames * (size_t)b->P.lg_frame));
     CU(cudaMalloc(&s.sb, fa * nch * 1152 * sizeof(double)));
     const size_t fa32 = (fa + 31) / 32 * 32; // frame-tile layouts are padded to whole tiles of 32 frames
     CU(cudaMalloc(&s.scalar_pre, fa32 * 192));
@@ -185,17 +194,28 @@ int alloc_slot(tlb_batch *b, Slot &s)
     }
     CU(cudaMalloc(&s.side, fa * sizeof(tlb_side)));
     CU(cudaMalloc(&s.d_peaks, (fa + 1) * 2 * sizeof(int16_t)));
-    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); // (kept when the slot grows:
+    if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));       //  slot 0's is the caller's handle)
+    s.cap = fa;
     return 0;
 }
 
-void free_slot(Slot &s)
+void free_buffers(Slot &s)
 {
+    cudaStream_t stream = s.stream;
+    cudaEvent_t done = s.done;
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
     cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
     cudaFree(s.p2_energy); cudaFree(s.p2_phi); cudaFree(s.p2_r); cudaFree(s.d_peaks);
+    s = Slot();
+    s.stream = stream;
+    s.done = done;
+}
+
+void free_slot(Slot &s)
+{
+    free_buffers(s);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s = Slot();
@@ -228,6 +248,16 @@ extern "C" {
 
 const char *tlb_last_error(void) { return g_err.c_str(); }
 
+int tlb_config_check(const tlb_config *cfg, tlb_info *info)
+{
+    if (!cfg) return fail(TLB_E_ARG, "NULL argument");
+    Mp2Params P;
+    tlb_info I;
+    const int rc = configure(*cfg, P, I);
+    if (!rc && info) *info = I;
+    return rc;
+}
+
 int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames)
 {
     if (!out || !cfg) return fail(TLB_E_ARG, "NULL argument");
@@ -245,8 +275,8 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
     if (!b) return fail(TLB_E_ARG, "out of memory");
     b->cfg = *cfg; b->P = P; b->info = I; b->device = device;
     b->chunk = max_chunk_frames ? max_chunk_frames : DEFAULT_CHUNK;
-    for (int i = 0; i < tlb_batch::NSLOT; i++)
-        if ((rc = alloc_slot(b, b->slot[i]))) { tlb_batch_destroy(b); return rc; }
+    // slot 0 now (its stream is the encoder's stream towards the caller), the others on first use
+    if ((rc = alloc_slot(b, b->slot[0], std::min(b->chunk, HOST_CHUNK)))) { tlb_batch_destroy(b); return rc; }
     {
         Mp2PsyTables T;
         std::memset(&T, 0, sizeof T);
@@ -307,6 +337,7 @@ void tlb_batch_destroy(tlb_batch *b)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
+    for (auto e : b->prof_events) cudaEventDestroy(e);
     cudaFree(b->d_tables);
     cudaFree(b->d_tables2);
     delete b;
@@ -326,7 +357,8 @@ int tlb_batch_sync(tlb_batch *b)
 {
     if (!b) return fail(TLB_E_ARG, "NULL argument");
     CU(cudaSetDevice(b->device));
-    for (auto &s : b->slot) CU(cudaStreamSynchronize(s.stream));
+    for (auto &s : b->slot)
+        if (s.stream) CU(cudaStreamSynchronize(s.stream));
     return 0;
 }
 
@@ -348,10 +380,13 @@ int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, si
     }
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
         Slot &s = b->slot[k % host_lanes];
+        if ((rc = alloc_slot(b, s, std::min(chunk, n_frames)))) return rc;
         const size_t n_out = std::min(chunk, n_frames - f0);
         const bool next_here = f0 + n_out < n_frames || has_next;
         const size_t fa = n_out + (next_here ? 1 : 0);
-        const size_t hist = std::min<size_t>(HALO, f0 * 1152 + history_samples);
+        size_t hist = std::min<size_t>(HALO, f0 * 1152 + history_samples);
+        if (nch == 1) hist &= ~(size_t)1; // keeps the staged region 4-byte aligned for k_gain_peak's sample pairs (the
+                                          // halo sizes are even, so an odd history always has a sample to spare)
         // (stream order makes re-use of the slot's buffers safe: the copies below queue behind its previous chunk)
         CU(cudaMemcpyAsync(s.d_pcm + (HALO - hist) * nch, pcm + (f0 * 1152 - hist) * nch,
                            (hist + fa * 1152) * nch * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
@@ -428,6 +463,8 @@ int tlb_batch_encode_device(tlb_batch *b, const int16_t *d_pcm, size_t n_frames,
     int lanes = b->profile ? 1 : (int)std::min<size_t>(n_chunks, 2); // per-kernel timing: one at a time
     if (const char *e = std::getenv("TLB_DEVICE_LANES")) // tuning knob
         lanes = b->profile ? 1 : std::max(1, std::min((int)std::min<size_t>(n_chunks, tlb_batch::NSLOT), std::atoi(e)));
+    for (int i = 0; i < lanes; i++)
+        if ((rc = alloc_slot(b, b->slot[i], std::min(b->chunk, n_frames)))) return rc;
     for (int i = 1; i < lanes; i++) {
         CU(cudaEventRecord(b->slot[0].done, b->slot[0].stream));
         CU(cudaStreamWaitEvent(b->slot[i].stream, b->slot[0].done, 0));

@@ -29,7 +29,8 @@ def test_bytes_equal_reference_golden(cfg, sig, n):
 
 
 STAGE_CASES = [(c, s) for c in ("A", "Bs", "Bj", "C", "T2j", "M48", "D", "L2", "E1") for s in ("S1", "S2", "S8")] + \
-              [("Bj", s) for s in ("S3", "S4", "S5", "S6", "S7")]
+              [("Bj", s) for s in ("S3", "S4", "S5", "S6", "S7")] + \
+              [(c, s) for c in ("R32", "R32s", "R32m", "R16", "R16j") for s in ("S2", "S6")]
 
 
 @pytest.mark.parametrize("cfg,sig", STAGE_CASES, ids=["%s-%s" % cs for cs in STAGE_CASES])
@@ -112,6 +113,63 @@ def test_streaming_dropin_matches_chunking_and_bytes(cfg, sig, psy):
         else:
             want.append(0)
     assert sizes == want and total[-1] == ref.size
+
+
+@pytest.mark.parametrize("cfg,psy,n", [("Bj", 1, 45), ("Bj", 2, 45), ("C", 1, 60), ("T2", 2, 70), ("H", 1, 12), ("L8", 1, 400),
+                                       ("E1", 2, 2), ("E1", 2, 1), ("Bj", 1, 8)])
+def test_streaming_dropin_with_xpad_records(cfg, psy, n):
+    """toolame_encode_frame(xpad_data, xpad_len, ...) as odr-audioenc calls it with ODR-PadEnc data
+    (toolame.c:515-551, src/odr-audioenc.cpp:823-852,1158): bytes and return sizes of the reference's 4096-byte
+    buffer, for psy models 1 and 2 (whose second frame looks back past the first), frame sizes from 48 to 1728
+    bytes and streams that end before / exactly at / after a flush."""
+    import odr_audioenc_b200 as tl
+    import signals
+    fs, mode, br = cases.CONFIGS[cfg]
+    nch = 1 if mode == "m" else 2
+    pcm = signals.make("S8", n, nch, fs)
+    pad_len = cases.PAD_LEN
+    xpad = cases.xpad_records(n, pad_len, seed=n + psy)
+    c = oracle.configure(fs, mode, br, psy, pad_len)
+    ref, _ = oracle.encode(c, pcm, xpad=xpad)
+    s = tl.ToolameStream(fs, mode, br, psy, pad_len)
+    chunks, sizes = [], []
+    for f in range(n):
+        b = s.encode_frame(pcm[f * 1152:(f + 1) * 1152], xpad_rec=xpad[f] if xpad[f, pad_len] else None)
+        sizes.append(b.size)
+        chunks.append(b)
+    assert tl.lib().toolame_b200_status() == 0
+    chunks.append(s.finish())
+    got = np.concatenate(chunks)
+    assert got.size == ref.size
+    bad = np.flatnonzero((got.reshape(n, -1) != ref.reshape(n, -1)).any(axis=1))
+    assert bad.size == 0, "frames differing: %s" % bad[:8]
+    held, want = 0, []
+    for f in range(n):
+        held += c.lg_frame
+        if held >= 4096:
+            want.append(4096 - (c.lg_frame + 4))
+            held -= want[-1]
+        else:
+            want.append(0)
+    assert sizes == want
+
+
+def test_dropin_restarts_cleanly():
+    """toolame_init after toolame_finish (and in mid-stream) starts a new stream with the zero history"""
+    import odr_audioenc_b200 as tl
+    import signals
+    pcm = signals.make("S1", 20, 2, 48000)
+    ref, _ = oracle.encode(oracle.configure(48000, "j", 128), pcm)
+    for _ in range(2):
+        s = tl.ToolameStream(48000, "j", 128)
+        got = [s.encode_frame(pcm[f * 1152:(f + 1) * 1152]) for f in range(20)] + [s.finish()]
+        assert np.array_equal(np.concatenate(got), ref)
+    s = tl.ToolameStream(48000, "j", 128)
+    for f in range(7):
+        s.encode_frame(pcm[f * 1152:(f + 1) * 1152])
+    s = tl.ToolameStream(48000, "j", 128)  # toolame_init in mid-stream
+    got = [s.encode_frame(pcm[f * 1152:(f + 1) * 1152]) for f in range(20)] + [s.finish()]
+    assert np.array_equal(np.concatenate(got), ref)
 
 
 def test_large_batch_properties():
