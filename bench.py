@@ -2,16 +2,25 @@
 """bench.py -- MP2 DAB encode throughput (audio-seconds encoded per second) on N B200s.
 
 Workload (BASELINE.json configs[1]): MP2 DAB 192 kbit/s, 48 kHz stereo, psy model 1, a 10 h synthetic PCM batch per
-GPU.  One step = one pass of the whole encode path over that batch.  Ranks hold independent streams (no
-collective on the data path; weak scaling), timing is max over ranks between barriers.
+GPU.  One step = one pass of the whole encode path over that batch.
 
-  value      device-resident: PCM already in HBM, frames written to HBM      (tlb_batch_encode_device)
-  e2e        through the C ABI with pinned HOST buffers, H2D/D2H inside      (tlb_batch_encode)
-  roofline   dominant kernel, CUDA-event time measured in the timed region on the launching stream
-  cpu_baseline  the reference libtoolame-dab (oracle/_ref/ref_driver, compiled unmodified) one process per host
-             core on a bounded sample of the same signal; falls back to the oracle port when _ref is absent
+  default      every rank encodes its own 10 h stream (weak scaling; no collective on the data path)
+  --strong     ONE stream of --hours, time-sharded over the ranks with PCM halo + look-ahead frame
+               (odr_audioenc_b200.sharding.time_shards); rank 0 gathers the pieces and byte-compares the
+               concatenation with its own single-GPU encode of the whole stream (strong scaling)
+  --config D   BASELINE configs[3]: 18 services x 1 h, sharded by service AND time (sharding.ensemble_shards),
+               same concatenation check (strong scaling)
+  --impl reference   the reference's own CPU implementation (oracle/_ref/ref_driver, compiled unmodified; the oracle
+               port when _ref is absent), one process per host core, each on a 120 s window cut from the SAME PCM
+               stream the GPU arm encodes
 
-`--impl reference` runs only that CPU arm (rank 0) and prints it in the same JSON shape.
+  value        device-resident: PCM already in HBM, frames written to HBM      (tlb_batch_encode_device)
+  e2e          through the C ABI with pinned HOST buffers, H2D/D2H inside      (tlb_batch_encode); next to it the
+               plain pinned-copy ceiling of the same bytes measured on all ranks at once
+  roofline     dominant kernel against the FP64 rate the path may use (DMUL+DADD, no FMA: the reference is built
+               without contraction), measured live; SURVEY 8(d) flops / bytes; CUDA-event time on the launching stream
+  cpu_baseline the reference arm's measurement, taken in the same run on rank 0
+  dropin       microseconds per frame through the reference's own API (toolame_encode_frame) beside the reference's
 """
 import argparse
 import json
@@ -30,57 +39,58 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CONFIGS = {"B": (48000, "j", 192, 2, 1, "MP2 DAB 192 kbit/s 48 kHz stereo (mode j), psy model 1"),
            "C": (24000, "m", 64, 1, 1, "MP2 DAB 64 kbit/s 24 kHz mono (LSF tables), psy model 1"),
            "E": (48000, "j", 256, 2, 2, "MP2 DAB 256 kbit/s 48 kHz joint stereo, psy model 2")}
-FS, MODE, KBPS, NCH, PSY, WORKLOAD = CONFIGS["B"]   # odr-audioenc's default mode for 2 channels is joint stereo
+ENSEMBLE = [(48000, "j", 192)] * 6 + [(48000, "j", 160)] * 4 + [(48000, "j", 128)] * 4 + [(48000, "j", 112)] * 2 + \
+           [(48000, "m", 96)] * 2   # BASELINE configs[3]: 18 MP2 services, mixed 96-192 kbit/s
 METRIC = "MP2 audio-seconds encoded/sec"
 UNIT = "audio-s/s"
-KERNEL_ALG = {}
+STREAM_SEED = 1000   # rank r of the weak-scaling run encodes stream STREAM_SEED + r; the reference arm cuts its windows from stream STREAM_SEED
 
 
-def select_config(name):
-    """algorithmic bytes and FP64 flops per frame (data-independent flops), per kernel: the bytes
-    a kernel must move for one frame and the FP64 operations it must do."""
-    global FS, MODE, KBPS, NCH, PSY, WORKLOAD, KERNEL_ALG
-    FS, MODE, KBPS, NCH, PSY, WORKLOAD = CONFIGS[name]
-    lg = (3 if FS == 48000 else 6) * KBPS
-    sbl = 27 if FS == 48000 else 30
-    KERNEL_ALG = {
-        "k_filterbank": (NCH * 1152 * 2 + NCH * 1152 * 8 + 192 + 96, NCH * 74844 + (2304 if MODE == "j" else 0)),
-        "k_spectrum": (NCH * (1024 * 2 + 2 * 512 * 8 + 128 + 256), NCH * 27334),
-        "k_label": (NCH * (2 * 512 * 8 + 128 + 1128), 0),
-        "k_threshold": (NCH * (1128 + 256 + 256) + 192, 0),
-        "k_spectrum2": (NCH * 2 * (1024 * 2 + 2 * 513 * 8), NCH * 2 * (1024 + 20488 + 2046)),
-        "k_psy2": (NCH * (4 * 2 * 513 * 8 + 256), NCH * 2 * 513 * 40),
-        "k_alloc": (192 + NCH * 32 * 8 + 336, 0),
-        "k_pack": (NCH * 1152 * 8 + 336 + 96 + lg, NCH * sbl * 36 * 4),
-    }
+class Cfg:
+    """One stream configuration and its SURVEY.md 8(d) algorithmic counts (data-independent FP64 flops; bytes = PCM
+    in + frame out)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.fs, self.mode, self.kbps, self.nch, self.psy, self.workload = CONFIGS[name]
+        self.lg = (3 if self.fs == 48000 else 6) * self.kbps
+        self.sblimit = 27 if self.fs == 48000 else 30
+        nch, js = self.nch, (2304 if self.mode == "j" else 0)
+        quant = self.sblimit * 36 * 4
+        if self.psy == 2:
+            psy = {"k_spectrum2": nch * 2 * (1024 + 20488 + 2046), "k_psy2": nch * (88000 - 2 * (1024 + 20488 + 2046))}
+        else:
+            psy = {"k_spectrum": nch * 27334}
+        self.kernel_flops = dict({"k_filterbank": nch * 74844 + js, "k_pack": nch * quant}, **psy)
+        self.flops_per_frame = sum(self.kernel_flops.values())     # B: 212 132 + 2 304
+        self.bytes_per_frame = nch * 1152 * 2 + self.lg            # B: 5 184
 
 
-select_config("B")
-
-# dram__bytes_read.sum + dram__bytes_write.sum per frame of config B, from the ncu --set full capture summarised in
-# profiles/ncu_r1_summary.md (end of round, launches of 75 777 frames); bench.py scales it to its own launch size
-NCU_DRAM_BYTES_PER_FRAME = {"k_filterbank": 22774, "k_spectrum": 20479, "k_label": 30285, "k_threshold": 1966,
-                            "k_alloc": 623, "k_pack": 19667}
-
-
-def synth_pcm_torch(n_frames, seed, device):
-    """S1-style signal of SURVEY.md 8(d) generated on the GPU in one-minute pieces (tones under a slow envelope,
-    a wandering 3 kHz component and noise); int16 (n_samples, 2)."""
+def synth_pcm(n0, n1, nch, fs, seed, device):
+    """Samples [n0, n1) of synthetic stream `seed`: the S1-style signal of SURVEY.md 8(d) (two tones under a slow
+    envelope, a wandering 3 kHz component, noise).  Every sample is a function of its absolute index only -- the noise
+    is a counter hash, not a generator state -- so any window of the stream can be produced on its own, on any rank,
+    and the reference arm encodes windows of exactly the PCM the GPU arm encodes.  int16 (n1 - n0, nch)."""
     import torch
-    n = n_frames * 1152
-    out = torch.empty((n, NCH), dtype=torch.int16, device=device)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    step = FS * 60
-    c = torch.arange(NCH, dtype=torch.float64, device=device)[None, :]
-    for s0 in range(0, n, step):
-        m = min(step, n - s0)
-        t = (torch.arange(s0, s0 + m, dtype=torch.float64, device=device) / FS)[:, None]
-        noise = torch.rand((m, NCH), generator=g, dtype=torch.float64, device=device) * 2 - 1
+    out = torch.empty((n1 - n0, nch), dtype=torch.int16, device=device)
+    step = 1 << 22
+    c = torch.arange(nch, dtype=torch.float64, device=device)[None, :]
+    ci = torch.arange(nch, dtype=torch.int64, device=device)[None, :]
+    for s0 in range(n0, n1, step):
+        s1 = min(s0 + step, n1)
+        idx = torch.arange(s0, s1, dtype=torch.int64, device=device)[:, None]
+        h = (idx * nch + ci + seed * 0x9E3779B1) & 0xFFFFFFFF      # 32-bit mix (xorshift-multiply), uniform in [0, 2^32)
+        h = ((h ^ (h >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+        h = ((h ^ (h >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+        h = h ^ (h >> 16)
+        noise = h.to(torch.float64) / 2147483648.0 - 1.0
+        t = idx.to(torch.float64) / fs
         env = 0.5 + 0.5 * torch.sin(2 * torch.pi * 0.37 * t)
         v = env * (0.3 * torch.sin(2 * torch.pi * (440 + 110 * c) * t)
                    + 0.2 * torch.sin(2 * torch.pi * (3000 + 500 * torch.sin(t)) * t)) + 0.05 * noise
-        out[s0:s0 + m] = torch.round(v * 32767 * 0.8).to(torch.int16)
+        out[s0 - n0:s1 - n0] = torch.round(v * 32767 * 0.8).to(torch.int16)
+    if out.is_cuda:
+        torch.cuda.synchronize(device)   # the encoder runs on its own streams: the PCM must be complete before it is handed over
     return out
 
 
@@ -141,277 +151,325 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[(len(sm) * 3) // 4], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(seconds_audio, n_procs, steps=1, warmup=0):
-    """The reference's own CPU implementation on a bounded sample: n_procs processes (one stream each, the
-    reference is not re-entrant) encode `seconds_audio` of the S1 signal concurrently.  Returns (per-step wall
-    seconds list, kind, frames per process)."""
-    import numpy as np
-    import signals
-    n_frames = int(seconds_audio * FS) // 1152
-    pcm = signals.make("S1", n_frames, NCH, FS)
-    ref_driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    times = []
-    with tempfile.TemporaryDirectory() as td:
-        pin = os.path.join(td, "in.pcm")
-        pcm.tofile(pin)
-        if os.path.exists(ref_driver):
-            kind = "reference"
-            cmd = [ref_driver, str(FS), MODE, str(KBPS), str(PSY), "0", pin, os.path.join(td, "out%d.mp2"), "--bench"]
-
-            def one_step():
-                t0 = time.perf_counter()
-                ps = [subprocess.Popen([c if "%d" not in c else c % i for c in cmd], stdout=subprocess.PIPE,
-                                       stderr=subprocess.DEVNULL, text=True) for i in range(n_procs)]
-                enc = [json.loads(p.communicate()[0])["seconds"] for p in ps]
-                wall = time.perf_counter() - t0
-                return max(enc), wall  # encode-loop time only (PCM preloaded), slowest process
-        else:
-            kind = "port"
-            import multiprocessing as mp
-
-            def one_step():
-                with mp.get_context("fork").Pool(n_procs) as pool:
-                    enc = pool.map(_oracle_worker, [pin] * n_procs)
-                return max(enc), max(enc)
-        for i in range(warmup + steps):
-            enc_s, _ = one_step()
-            if i >= warmup:
-                times.append(enc_s)
-    return times, kind, n_frames
+# ------------------------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU implementation on windows of the GPU arm's stream
+# ------------------------------------------------------------------------------------------------------------------
+def reference_windows(cfg, n_frames_total, cores, sample_seconds):
+    """(first frame, frames) of the window each host core encodes: `cores` windows of sample_seconds, spread evenly
+    over the stream the GPU arm's rank 0 encodes."""
+    nf = max(1, min(int(sample_seconds * cfg.fs) // 1152, n_frames_total))
+    stride = max(1, (n_frames_total - nf) // max(1, cores - 1)) if cores > 1 else 0
+    return [(min(k * stride, n_frames_total - nf), nf) for k in range(cores)]
 
 
-def _oracle_worker(pin):
+def _oracle_worker(job):
     import numpy as np
     import oracle
-    pcm = np.fromfile(pin, dtype=np.int16).reshape(-1, NCH)
-    c = oracle.configure(FS, MODE, KBPS, PSY)
+    path, fs, mode, kbps, psy, nch = job
+    pcm = np.fromfile(path, dtype=np.int16).reshape(-1, nch)
+    c = oracle.configure(fs, mode, kbps, psy)
     t0 = time.perf_counter()
     oracle.encode(c, pcm)
     return time.perf_counter() - t0
 
 
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def cpu_reference_run(cfg, windows_pcm, steps=1, warmup=0):
+    """windows_pcm: one int16 array (samples, nch) per host core.  All windows are encoded concurrently, one process
+    per core (the reference keeps its state in statics: one stream per process).  Returns (per-step seconds of the
+    slowest process' encode loop, kind)."""
+    ref_driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    times = []
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        paths = []
+        for i, w in enumerate(windows_pcm):
+            paths.append(os.path.join(td, "in%d.pcm" % i))
+            w.tofile(paths[-1])
+        if os.path.exists(ref_driver):
+            kind = "reference"
+
+            def one_step():
+                ps = [subprocess.Popen([ref_driver, str(cfg.fs), cfg.mode, str(cfg.kbps), str(cfg.psy), "0", p,
+                                        os.path.join(td, "out%d.mp2" % i), "--bench"], stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True) for i, p in enumerate(paths)]
+                return max(json.loads(p.communicate()[0])["seconds"] for p in ps)  # encode loop only (PCM preloaded)
+        else:
+            kind = "port"
+            import multiprocessing as mp
+
+            def one_step():
+                with mp.get_context("fork").Pool(len(paths)) as pool:
+                    return max(pool.map(_oracle_worker, [(p, cfg.fs, cfg.mode, cfg.kbps, cfg.psy, cfg.nch) for p in paths]))
+        for i in range(warmup + steps):
+            t = one_step()
+            if i >= warmup:
+                times.append(t)
+    return times, kind
+
+
+def workload_config(cfg, args, n_frames):
+    """The `config` object of the JSON line -- identical in both arms (the reference arm encodes a bounded sample of
+    this workload and says so in cpu_baseline.sample)."""
+    return {"workload": "%s, %.3g h synthetic PCM batch per GPU (%d frames, %.2f GB of PCM: larger than L2)"
+                        % (cfg.workload, args.hours, n_frames, n_frames * 1152 * cfg.nch * 2 / 1e9),
+            "frames_per_gpu": n_frames, "pcm": "synth_pcm stream %d (+rank), hash noise: any window reproducible" % STREAM_SEED}
+
+
+def run_reference_arm(args, cfg):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    import torch
     cores = os.cpu_count() or 1
-    sample_s = args.cpu_sample_seconds
-    times, kind, n_frames = cpu_reference_run(sample_s, cores, steps=args.steps, warmup=min(args.warmup, 1))
-    audio_s = n_frames * 1152 / FS * cores
+    n_frames = int(round(args.hours * 3600 * cfg.fs / 1152))
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    wins = reference_windows(cfg, n_frames, cores, args.cpu_sample_seconds)
+    pcm = [synth_pcm(f0 * 1152, (f0 + nf) * 1152, cfg.nch, cfg.fs, STREAM_SEED, dev).cpu().numpy() for f0, nf in wins]
+    times, kind = cpu_reference_run(cfg, pcm, steps=args.steps, warmup=min(args.warmup, 1))
+    nf = wins[0][1]
+    audio_s = nf * 1152 / cfg.fs * cores
     t = sum(times) / len(times)
     value = audio_s / t
-    line = {
+    print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD + "; per step a bounded sample of the "
-                               "10 h batch: %.0f s of audio per host core, %d cores" % (n_frames * 1152 / FS, cores)},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, args, n_frames),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": "%d processes x %d frames (%.0f s) of signal S1, encode loop only" % (cores, n_frames, n_frames * 1152 / FS)},
+                         "us_per_frame_per_core": t / nf * 1e6,
+                         "sample": "%d processes x %d frames (%.0f s), windows spread over rank 0's stream (same PCM as the "
+                                   "GPU arm), encode loop only" % (cores, nf, nf * 1152 / cfg.fs)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+        "gpu_launches": 0}))
 
 
-ENSEMBLE = [(48000, "j", 192)] * 6 + [(48000, "j", 160)] * 4 + [(48000, "j", 128)] * 4 + [(48000, "j", 112)] * 2 + \
-           [(48000, "m", 96)] * 2   # BASELINE configs[3]: 18 MP2 services, mixed 96-192 kbit/s
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm helpers
+# ------------------------------------------------------------------------------------------------------------------
+class Dist:
+    """rank / world plumbing: torch.distributed is used for barriers, max-over-ranks and the parity gather only"""
 
+    def __init__(self):
+        import torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (this implementation has no CPU path)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else "single rank: not bound"
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
 
-def run_ensemble(args):
-    """--config D: the 18-service ensemble, `--hours` of audio per service, sharded by whole services across the
-    ranks (odr_audioenc_b200.sharding.service_shards: LPT by a bitrate-weighted cost).  Fixed total work: strong
-    scaling.  Device-resident value and end-to-end (pinned host buffers) like the main mode."""
-    import ctypes as C
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import odr_audioenc_b200 as tl
-    from odr_audioenc_b200 import sharding
-    global FS, NCH
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    n_frames = int(round(args.hours * 3600 * 48000 / 1152))
-    plan = sharding.service_shards([(fs, 1 if m == "m" else 2, br, n_frames) for fs, m, br in ENSEMBLE], world)
-    mine = plan[rank]
-    L = tl.lib()
-    encs, work = {}, []
-    for i in mine:
-        fs, mode, br = ENSEMBLE[i]
-        key = (fs, mode, br)
-        if key not in encs:
-            encs[key] = tl.BatchEncoder(fs, mode, br, 1, 0, local, args.chunk_frames or 148 * 256)
-        e = encs[key]
-        FS, NCH = fs, e.nch
-        d_pcm = synth_pcm_torch(n_frames, 5000 + i, dev)
-        d_out = torch.empty(n_frames * e.lg_frame, dtype=torch.uint8, device=dev)
-        work.append((e, d_pcm, d_out))
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        for e, d_pcm, d_out in work:
-            e.encode_device(d_pcm.data_ptr(), n_frames, 0, False, None, d_out.data_ptr())
-        for e in encs.values():
-            e.sync()
+    def allmax(self, x):
+        return self._reduce(x, "MAX")
 
-    h_bufs = []
-    for e, d_pcm, d_out in work:
-        hp, ho = L.tlb_host_alloc(d_pcm.numel() * 2), L.tlb_host_alloc(d_out.numel())
-        h_pcm = np.ctypeslib.as_array((C.c_int16 * d_pcm.numel()).from_address(hp)).reshape(-1, e.nch)
-        h_out = np.ctypeslib.as_array((C.c_uint8 * d_out.numel()).from_address(ho))
-        torch.from_numpy(h_pcm).copy_(d_pcm)
-        h_bufs.append((h_pcm, h_out))
-    L.tlb_batch_encode_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    def allmin(self, x):
+        return self._reduce(x, "MIN")
 
-    def step_host():
-        for (e, _, _), (h_pcm, h_out) in zip(work, h_bufs):
-            L.tlb_batch_encode_async(e._h, h_pcm.ctypes.data, n_frames, 0, 0, None, h_out.ctypes.data)
-        for e in encs.values():
-            e.sync()
+    def allsum(self, x):
+        return self._reduce(x, "SUM")
 
-    def timed(fn):
-        for _ in range(args.warmup):
-            fn()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            fn()
-        torch.cuda.synchronize()
-        t = time.perf_counter() - t0
-        barrier()
-        if world > 1:
-            tt = torch.tensor([t], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t = float(tt.item())
-        return t
-
-    launches0 = sum(e.launches for e in encs.values())
-    t_dev = timed(step_device)
-    launches = (sum(e.launches for e in encs.values()) - launches0) // (args.steps + args.warmup)
-    t_host = timed(step_host)
-    same = all(bool(torch.equal(torch.from_numpy(h_out[:4096]).to(dev), d_out[:4096])) for (_, _, d_out), (_, h_out) in zip(work, h_bufs))
-    if rank == 0:
-        audio = len(ENSEMBLE) * n_frames * 1152 / 48000
-        print(json.dumps({
-            "metric": METRIC, "value": audio * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "DAB ensemble: 18 MP2 services x %.3g h, 6x192 4x160 4x128 2x112 kbit/s joint stereo + 2x96 mono, "
-                                   "psy model 1, whole services per GPU (LPT)" % args.hours, "plan": plan},
-            "e2e": {"value": audio * args.steps / t_host, "unit": UNIT,
-                    "h2d_bytes_per_step": sum(int(n_frames * 1152 * (1 if m == "m" else 2) * 2) for _, m, _ in ENSEMBLE),
-                    "d2h_bytes_per_step": sum(int(n_frames * 3 * br) for _, _, br in ENSEMBLE)},
-            "gpu_launches": int(launches * args.steps), "host_equals_device_outputs": same}))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--hours", type=float, default=10.0, help="audio per GPU per step (BASELINE config: 10 h)")
-    ap.add_argument("--config", default="B", choices=sorted(CONFIGS) + ["D"], help="B = BASELINE configs[1] (default), C = configs[2], E = configs[4]")
-    ap.add_argument("--chunk-frames", type=int, default=0)
-    ap.add_argument("--cpu-sample-seconds", type=float, default=120.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 0)
-    if args.config == "D":
-        if args.impl == "reference":
-            raise SystemExit("--config D has no reference arm (use the default config)")
-        if args.hours == 10.0:
-            args.hours = 1.0  # BASELINE configs[3]: 1 h per service
-        return run_ensemble(args)
-    select_config(args.config)
-    if args.impl == "reference":
-        return run_reference_arm(args)
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import odr_audioenc_b200 as tl
-    import ctypes as C
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    n_frames = int(round(args.hours * 3600 * FS / 1152))
-    enc = tl.BatchEncoder(FS, MODE, KBPS, PSY, 0, local, args.chunk_frames)
-    lg = enc.lg_frame
-    L = tl.lib()
-
-    # ---- inputs: resident in HBM (value) and in pinned host memory (e2e)
-    d_pcm = synth_pcm_torch(n_frames, 1000 + rank, dev)
-    d_out = torch.empty(n_frames * lg, dtype=torch.uint8, device=dev)
-    pcm_bytes, out_bytes = d_pcm.numel() * 2, d_out.numel()
-
-    def step_device():
-        enc.encode_device(d_pcm.data_ptr(), n_frames, 0, False, None, d_out.data_ptr())
-
-    stream = torch.cuda.ExternalStream(enc.stream, device=dev)
-
-    def timed(fn, steps, warmup, sync_each):
-        """max-over-ranks seconds for `steps` steps, device-timed with CUDA events on the encoder's stream"""
-        for _ in range(warmup):
-            fn()
-            enc.sync()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-            if sync_each:
-                enc.sync()
-        e1.record(stream)
-        enc.sync()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        dev_s = e0.elapsed_time(e1) * 1e-3
-        barrier()
-        return dev_s, wall
-
-    def allmax(x):
-        if world == 1:
+    def _reduce(self, x, op):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+def timed(D, fn, sync, steps, warmup, stream=None):
+    """(device seconds by CUDA events on `stream` if given, wall seconds) for `steps` calls of fn, max over ranks;
+    barrier + synchronize on both sides"""
+    import torch
+    for _ in range(warmup):
+        fn()
+        sync()
+    D.barrier()
+    dev_s = None
+    if stream is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    if stream is not None:
+        e1.record(stream)
+    sync()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if stream is not None:
+        dev_s = D.allmax(e0.elapsed_time(e1) * 1e-3)
+    D.barrier()
+    return dev_s, D.allmax(wall)
+
+
+def pinned_array(L, nbytes, dtype, shape):
+    import ctypes as C
+    import numpy as np
+    p = L.tlb_host_alloc(max(nbytes, 16))
+    if not p:
+        raise SystemExit("bench.py: pinned host allocation failed")
+    n = nbytes // np.dtype(dtype).itemsize
+    ct = {1: C.c_uint8, 2: C.c_int16}[np.dtype(dtype).itemsize]
+    return np.ctypeslib.as_array((ct * max(n, 1)).from_address(p))[:n].view(dtype).reshape(shape)
+
+
+def copy_ceiling(D, h_in, d_in, h_out, d_out, steps):
+    """Plain pinned copies of one step's bytes -- H2D of the PCM and D2H of the frames on two streams, all ranks at
+    once, no kernels: what the host side of the box allows the end-to-end path.  Returns seconds per step (max over
+    ranks)."""
+    import torch
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    t_in, t_out = torch.from_numpy(h_in), torch.from_numpy(h_out)
+
+    def one():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(t_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            t_out.copy_(d_out, non_blocking=True)
+
+    one()
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    D.barrier()
+    return D.allmax(t) / steps
+
+
+def oracle_windows_check(cfg, d_pcm, d_out, n_frames, first_frame=0, has_next=False, n_windows=16, win=32):
+    """The CUDA output against the oracle (the checker, never the thing measured) on n_windows windows of `win`
+    frames spread over the whole batch.  d_pcm row 0 = first sample of local frame 0, whose stream index is
+    first_frame; has_next: the PCM holds one more frame after the last one encoded (a time shard).  The oracle
+    starts every segment with zero history, so a window is handed `lead` extra frames in front (then its frames see
+    their true halo: 480 samples, 1632 with psy model 2) -- except at the very start of the stream, where zero history
+    is the truth.  Returns (frames checked, frames byte-identical)."""
+    import oracle
+    lead = 2
+    ocfg = oracle.configure(cfg.fs, cfg.mode, cfg.kbps, cfg.psy)
+    lg = cfg.lg
+    win = min(win, n_frames)
+    n_windows = max(1, min(n_windows, n_frames // (win + lead + 1)))
+    checked = same = 0
+    for k in range(n_windows):
+        f0 = (n_frames - win) * k // (n_windows - 1) if n_windows > 1 else 0
+        if f0 < lead:
+            f0, ld = (0, 0) if first_frame == 0 else (min(lead, n_frames - win), min(lead, n_frames - win))
+        else:
+            ld = lead
+        more = 0 if (f0 + win >= n_frames and not has_next) else 1   # the stream's last frame keeps its own ScF-CRC
+        seg = d_pcm[(f0 - ld) * 1152:(f0 + win + more) * 1152].cpu().numpy()
+        want, _ = oracle.encode(ocfg, seg, ld, ld + win)
+        got = d_out[f0 * lg:(f0 + win) * lg].cpu().numpy()
+        same += int((got.reshape(win, -1) == want.reshape(win, -1)).all(axis=1).sum())
+        checked += win
+    return checked, same
+
+
+def load_traffic(config_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per frame and kernel from the committed ncu capture
+    (tools/ncu_traffic.py writes profiles/ncu_r2_traffic.json from `ncu --set full`); None when absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_r2_traffic.json")))
+        return t.get(config_name), t.get("source")
+    except (OSError, ValueError):
+        return None, None
+
+
+def fp64_peaks(L, local):
+    import ctypes as C
+    dfma, dmuladd = C.c_double(), C.c_double()
+    L.tlb_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tlb_fp64_peak(local, C.byref(dfma), C.byref(dmuladd))
+    return dfma.value, dmuladd.value
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dropin_rate(cfg, pcm_host, n_frames):
+    """microseconds per frame through the reference's own streaming API (toolame_encode_frame), wall clock"""
+    import numpy as np
+    import odr_audioenc_b200 as tl
+    s = tl.ToolameStream(cfg.fs, cfg.mode, cfg.kbps, cfg.psy)
+    planar = np.zeros((n_frames, 2, 1152), dtype=np.int16)
+    planar[:, :cfg.nch] = pcm_host[:n_frames * 1152].reshape(n_frames, 1152, cfg.nch).transpose(0, 2, 1)
+    L, out = tl.lib(), np.zeros(4092, dtype=np.uint8)
+    for f in range(min(64, n_frames)):   # warm-up: encoder creation, first launches
+        L.toolame_encode_frame(planar[f].ctypes.data, None, 0, out.ctypes.data, out.size)
+    t0 = time.perf_counter()
+    total = 0
+    for f in range(n_frames):
+        total += L.toolame_encode_frame(planar[f].ctypes.data, None, 0, out.ctypes.data, out.size)
+    t = time.perf_counter() - t0
+    total += L.toolame_finish(out.ctypes.data, out.size)
+    return t / n_frames * 1e6, total
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# default mode (weak scaling) and --strong (one stream, time-sharded)
+# ------------------------------------------------------------------------------------------------------------------
+def run_stream(args, cfg):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import odr_audioenc_b200 as tl
+    from odr_audioenc_b200 import sharding
+
+    D = Dist()
+    L = tl.lib()
+    n_total = int(round(args.hours * 3600 * cfg.fs / 1152))
+    if args.strong:
+        rng = sharding.time_shards(n_total, D.world, psy_model=cfg.psy)[D.rank]
+        seed = STREAM_SEED
+    else:
+        rng = sharding.FrameRange(0, n_total, 0, False)
+        seed = STREAM_SEED + D.rank
+    n_frames = rng.f1 - rng.f0
+    first, end = sharding.pcm_slice(rng)
+    hist = rng.history_samples
+    enc = tl.BatchEncoder(cfg.fs, cfg.mode, cfg.kbps, cfg.psy, 0, D.local, args.chunk_frames)
+    lg = enc.lg_frame
+    assert lg == cfg.lg
+
+    # ---- inputs: resident in HBM (value) and in pinned host memory (e2e); row `hist` = first sample to encode
+    d_pcm = synth_pcm(first, end, cfg.nch, cfg.fs, seed, D.dev)
+    d_out = torch.empty(n_frames * lg, dtype=torch.uint8, device=D.dev)
+    pcm_bytes, out_bytes = d_pcm.numel() * 2, d_out.numel()
+    d_first = d_pcm.data_ptr() + hist * cfg.nch * 2
+
+    def step_device():
+        enc.encode_device(d_first, n_frames, hist, rng.has_next, None, d_out.data_ptr())
+
+    stream = torch.cuda.ExternalStream(enc.stream, device=D.dev)
+    sampler = ClockSampler(D.local) if D.rank == 0 else None
     if sampler:
         sampler.start()
     launches0 = enc.launches
-    dev_s, _ = timed(step_device, args.steps, args.warmup, sync_each=False)
+    dev_s, _ = timed(D, step_device, enc.sync, args.steps, args.warmup, stream)
     launches_per_step = (enc.launches - launches0) // (args.steps + args.warmup)
     # second timed region, same work: CUDA events around every kernel on the launching stream.  Chunks are not
     # overlapped across streams here, so each kernel's time is its own (the roofline wants a kernel timed alone).
@@ -421,121 +479,292 @@ def main():
     L.tlb_batch_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.tlb_batch_profile(enc._h, 1)
     prof_steps = max(1, min(args.steps, 2))
-    serial_s, _ = timed(step_device, prof_steps, 1, sync_each=False)
+    serial_s, _ = timed(D, step_device, enc.sync, prof_steps, 1, stream)
     L.tlb_batch_kernel_times(enc._h, ms, cnt)
     L.tlb_batch_profile(enc._h, 0)
     if sampler:
         sampler.stop()
-    dev_s = allmax(dev_s)
-    audio_s_total = world * n_frames * 1152 / FS
+    audio_s_total = (n_total if args.strong else n_total * D.world) * 1152 / cfg.fs
     value = audio_s_total * args.steps / dev_s
 
-    # ---- e2e through the host-buffer entry point (pinned memory, copies inside the timed region)
-    e2e = None
+    # ---- e2e through the host-buffer entry point (pinned memory, copies inside the timed region), and the plain-copy
+    # ceiling of the same bytes on all ranks at once
+    e2e, h_pcm = None, None
     if not args.no_e2e:
-        h_pcm_p = L.tlb_host_alloc(pcm_bytes)
-        h_out_p = L.tlb_host_alloc(out_bytes)
-        if not h_pcm_p or not h_out_p:
-            raise SystemExit("bench.py: pinned host allocation failed")
-        h_pcm = np.ctypeslib.as_array((C.c_int16 * (pcm_bytes // 2)).from_address(h_pcm_p)).reshape(-1, NCH)
-        h_out = np.ctypeslib.as_array((C.c_uint8 * out_bytes).from_address(h_out_p))
+        h_pcm = pinned_array(L, pcm_bytes, np.int16, (-1, cfg.nch))
+        h_out = pinned_array(L, out_bytes, np.uint8, (-1,))
         torch.from_numpy(h_pcm).copy_(d_pcm)  # same signal, now on the host
         torch.cuda.synchronize()
 
         def step_host():
-            enc.encode(h_pcm, n_frames=n_frames, out=h_out)
+            enc.encode(h_pcm, n_frames=n_frames, history=hist, has_next=rng.has_next, out=h_out)
 
-        _, wall = timed(step_host, args.steps, args.warmup, sync_each=True)
-        wall = allmax(wall)
-        e2e = {"value": audio_s_total * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes * world,
-               "d2h_bytes_per_step": out_bytes * world}
-        # the two paths must agree byte for byte
-        same = bool(torch.equal(torch.from_numpy(h_out[:lg * 4096]).to(dev), d_out[:lg * 4096]))
-        if not same:
+        _, wall = timed(D, step_host, enc.sync, args.steps, args.warmup)
+        # the two paths must agree byte for byte: the whole output, compared on the device
+        same = bool(torch.equal(torch.from_numpy(h_out).to(D.dev), d_out))
+        if D.allmin(1.0 if same else 0.0) < 1.0:
             raise SystemExit("bench.py: host-buffer and device-resident outputs differ")
+        d_scratch = torch.empty_like(d_pcm)
+        t_copy = copy_ceiling(D, h_pcm, d_scratch, h_out, d_out.clone(), max(2, args.steps))
+        del d_scratch
+        tot_in, tot_out = D.allsum(float(pcm_bytes)), D.allsum(float(out_bytes))
+        e2e = {"value": audio_s_total * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(tot_in),
+               "d2h_bytes_per_step": int(tot_out), "host_equals_device_output": "all %d bytes" % out_bytes,
+               "copy_ceiling": {"value": audio_s_total / t_copy, "unit": UNIT, "h2d_gbs": tot_in / t_copy / 1e9,
+                                "d2h_gbs": tot_out / t_copy / 1e9,
+                                "what": "plain pinned cudaMemcpyAsync of the same bytes, H2D and D2H on two streams, all ranks at once"},
+               }
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling"]["value"]
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    # ---- parity: oracle windows spread over this rank's frames (every rank checks its own, rank 0 reports the sum)
+    checked, same = oracle_windows_check(cfg, d_pcm[hist:], d_out, n_frames, rng.f0, rng.has_next, args.parity_windows)
+    checked_all, same_all = D.allsum(float(checked)), D.allsum(float(same))
+    parity = {"frames": int(checked_all), "byte_identical_to_oracle": int(same_all),
+              "windows": "%d windows x 32 frames per rank, spread over the whole batch" % (checked // 32)}
+
+    # ---- --strong: gather the pieces on rank 0 and byte-compare the concatenation with the single-GPU encode
+    if args.strong and D.world > 1:
+        import torch.distributed as dist
+        shards = sharding.time_shards(n_total, D.world, psy_model=cfg.psy)
+        biggest = max(s.f1 - s.f0 for s in shards) * lg
+        mine = torch.zeros(biggest, dtype=torch.uint8, device=D.dev)
+        mine[:out_bytes] = d_out
+        parts = [torch.empty(biggest, dtype=torch.uint8, device=D.dev) for _ in range(D.world)] if D.rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if D.rank == 0:
+            whole_pcm = synth_pcm(0, n_total * 1152, cfg.nch, cfg.fs, seed, D.dev)
+            whole = torch.empty(n_total * lg, dtype=torch.uint8, device=D.dev)
+            enc.encode_device(whole_pcm.data_ptr(), n_total, 0, False, None, whole.data_ptr())
+            enc.sync()
+            cat = torch.cat([p[:(s.f1 - s.f0) * lg] for p, s in zip(parts, shards)])
+            parity["concatenation_equals_single_gpu"] = bool(torch.equal(cat, whole))
+            parity["concatenation_bytes"] = int(cat.numel())
+            del whole_pcm, whole, cat, parts
+
+    if D.rank != 0:
+        D.close()
         return
-
-    # ---- parity spot check against the oracle (the checker, never the thing measured)
-    import oracle
-    chk_f0, chk_n = n_frames // 2, 64
-    lead = 2  # leading frames: the oracle starts its history at the segment start; frames `lead`.. then see their true
-    #           halo (480 samples for the filterbank and psy model 1, 1632 = two blocks back for psy model 2)
-    seg = d_pcm[(chk_f0 - lead) * 1152:(chk_f0 + chk_n + 1) * 1152].cpu().numpy()
-    ocfg = oracle.configure(FS, MODE, KBPS, PSY)
-    want, _ = oracle.encode(ocfg, seg, lead, lead + chk_n)
-    got = d_out[chk_f0 * lg:(chk_f0 + chk_n) * lg].cpu().numpy()
-    parity_frames_equal = int((got.reshape(chk_n, -1) == want.reshape(chk_n, -1)).all(axis=1).sum())
 
     # ---- roofline of the dominant kernel
     L.tlb_batch_kernel_name.restype = C.c_char_p
     L.tlb_batch_kernel_name.argtypes = [C.c_void_p, C.c_int]
     names = [L.tlb_batch_kernel_name(enc._h, k).decode() or "unused%d" % k for k in range(NK)]
+    dfma, dmuladd = fp64_peaks(L, D.local)
+    hbm, hbm_src = hbm_peak()
+    traffic, traffic_src = load_traffic(cfg.name)
+    launched = n_frames * (prof_steps + 1)   # frames each kernel processed in the profiled region (incl. its warm-up step)
     per_kernel = {}
     total_ms = sum(ms[k] for k in range(NK)) or 1.0
     for k in range(NK):
-        n_l = max(int(cnt[k]), 1)
-        per_kernel[names[k]] = {"launches": int(cnt[k]), "avg_ms": ms[k] / n_l, "share": ms[k] / total_ms}
-    top = max(range(NK), key=lambda k: ms[k])
-    frames_per_launch = n_frames * (prof_steps + 1) / max(int(cnt[top]), 1)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    kb, kf = KERNEL_ALG.get(names[top], (0, 0))
-    dur_s = per_kernel[names[top]]["avg_ms"] * 1e-3
-    achieved_gbs = kb * frames_per_launch / dur_s / 1e9
-    dfma, dmuladd = C.c_double(), C.c_double()
-    L.tlb_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    L.tlb_fp64_peak(local, C.byref(dfma), C.byref(dmuladd))
-    for name, rec in per_kernel.items():  # every kernel against both rooflines (algorithmic bytes / flops per launch)
-        kb_k, kf_k = KERNEL_ALG.get(name, (0, 0))
-        if rec["launches"] and rec["avg_ms"] > 0:
-            fpl = n_frames * (prof_steps + 1) / rec["launches"]
-            rec["hbm_gbs"] = kb_k * fpl / (rec["avg_ms"] * 1e-3) / 1e9
-            rec["hbm_frac"] = rec["hbm_gbs"] / hbm_peak
-            rec["fp64_tflops"] = kf_k * fpl / (rec["avg_ms"] * 1e-3) / 1e12
-            rec["fp64_frac_of_no_fma_peak"] = rec["fp64_tflops"] / dmuladd.value if dmuladd.value > 0 else None
-    roofline = {"kernel": names[top], "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak,
-                "traffic": (NCU_DRAM_BYTES_PER_FRAME.get(names[top]) * frames_per_launch
-                            if args.config == "B" and names[top] in NCU_DRAM_BYTES_PER_FRAME else None),
-                "traffic_source": "ncu --set full, profiles/ncu_r1_summary.md (per frame x frames per launch)",
-                "algorithmic_bytes": kb * frames_per_launch, "peak_source": peak_src,
-                "fp64": {"achieved_tflops": kf * frames_per_launch / dur_s / 1e12, "peak_dmul_dadd_tflops": dmuladd.value,
-                         "peak_dfma_tflops": dfma.value,
-                         "frac_of_no_fma_peak": (kf * frames_per_launch / dur_s / 1e12) / dmuladd.value if dmuladd.value > 0 else None},
-                "kernels": per_kernel, "serialised_ms_per_step": serial_s / prof_steps * 1e3,
-                "frames_per_launch": frames_per_launch}
+        if not cnt[k] or names[k].startswith("unused"):
+            continue
+        avg_s = ms[k] / cnt[k] * 1e-3
+        fpl = launched / cnt[k]
+        fl = cfg.kernel_flops.get(names[k], 0)
+        rec = {"launches": int(cnt[k]), "avg_ms": avg_s * 1e3, "share": ms[k] / total_ms, "ns_per_frame": avg_s / fpl * 1e9,
+               "fp64_tflops": fl * fpl / avg_s / 1e12, "fp64_frac": fl * fpl / avg_s / 1e12 / dmuladd if dmuladd > 0 else None}
+        if traffic and names[k] in traffic:
+            rec["dram_bytes_per_frame_ncu"] = traffic[names[k]]
+        per_kernel[names[k]] = rec
+    top = max(per_kernel, key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["launches"])
+    tk = per_kernel[top]
+    fpl = launched / tk["launches"]
+    step_s = dev_s / args.steps
+    path_tflops = cfg.flops_per_frame * n_frames / step_s / 1e12
+    roofline = {
+        "kernel": top, "bound": "fp64", "achieved": tk["fp64_tflops"], "peak": dmuladd, "unit": "TFLOP/s",
+        "frac": tk["fp64_tflops"] / dmuladd if dmuladd > 0 else None,
+        "peak_source": "measured live by tlb_fp64_peak: independent DMUL+DADD chains (the path may not use FMA: the "
+                       "reference is built without contraction); DFMA chains reach %.2f TFLOP/s; MEASURED_PEAKS.json holds no FP64 figure" % dfma,
+        "algorithmic_flops": cfg.kernel_flops.get(top, 0) * fpl, "algorithmic_bytes": cfg.bytes_per_frame * fpl,
+        "traffic": traffic[top] * fpl if traffic and top in traffic else None,
+        "traffic_source": traffic_src,
+        "hbm": {"achieved": cfg.bytes_per_frame * fpl / (tk["avg_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": cfg.bytes_per_frame * fpl / (tk["avg_ms"] * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
+                "what": "SURVEY 8(d) bytes per frame (PCM in + frame out = %d) x frames per launch / kernel time" % cfg.bytes_per_frame},
+        "path": {"flops_per_frame": cfg.flops_per_frame, "bytes_per_frame": cfg.bytes_per_frame,
+                 "achieved_tflops": path_tflops, "frac": path_tflops / dmuladd if dmuladd > 0 else None,
+                 "hbm_gbs": cfg.bytes_per_frame * n_frames / step_s / 1e9,
+                 "hbm_frac": cfg.bytes_per_frame * n_frames / step_s / 1e9 / hbm,
+                 "dram_bytes_per_frame_ncu": sum(traffic[k] for k in per_kernel if k in traffic) if traffic else None,
+                 "what": "whole step (all kernels, chunks overlapped on two streams) against the same peaks"},
+        "kernels": per_kernel, "serialised_ms_per_step": serial_s / prof_steps * 1e3, "frames_per_launch": fpl}
 
+    # ---- the reference on this box's host cores, on windows of rank 0's stream (weak mode: this very PCM)
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times, kind, nf = cpu_reference_run(args.cpu_sample_seconds, cores)
-        cpu_baseline = {"value": nf * 1152 / FS * cores / times[0], "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": "%d processes x %d frames (%.0f s) of signal S1, encode loop only" % (cores, nf, nf * 1152 / FS)}
+        if args.strong and D.world > 1:
+            wins = reference_windows(cfg, n_total, cores, args.cpu_sample_seconds)
+            wp = [synth_pcm(f0 * 1152, (f0 + nf) * 1152, cfg.nch, cfg.fs, seed, D.dev).cpu().numpy() for f0, nf in wins]
+        else:
+            wins = reference_windows(cfg, n_frames, cores, args.cpu_sample_seconds)
+            wp = [d_pcm[(hist + f0 * 1152):(hist + (f0 + nf) * 1152)].cpu().numpy() for f0, nf in wins]
+        times, kind = cpu_reference_run(cfg, wp)
+        nf = wins[0][1]
+        cpu_baseline = {"value": nf * 1152 / cfg.fs * cores / times[0], "unit": UNIT, "cores": cores, "kind": kind,
+                        "us_per_frame_per_core": times[0] / nf * 1e6,
+                        "sample": "%d processes x %d frames (%.0f s), windows spread over rank 0's stream (same PCM as the "
+                                  "GPU arm), encode loop only" % (cores, nf, nf * 1152 / cfg.fs)}
+    dropin = None
+    if not args.no_dropin:
+        nfd = min(n_frames, 3000)
+        us, nbytes = dropin_rate(cfg, d_pcm[hist:hist + nfd * 1152].cpu().numpy(), nfd)
+        dropin = {"us_per_frame": us, "x_realtime": 1152 / cfg.fs / (us * 1e-6), "frames": nfd, "bytes": int(nbytes),
+                  "what": "toolame_encode_frame (the reference's own streaming API, one stream, wall clock, copies included)",
+                  "reference_us_per_frame_per_core": cpu_baseline["us_per_frame_per_core"] if cpu_baseline else None}
 
+    config = workload_config(cfg, args, n_total)
+    if args.strong:
+        config["workload"] = "%s, ONE %.3g h stream (%d frames) time-sharded over %d GPU(s) with PCM halo and look-ahead frame" \
+                             % (cfg.workload, args.hours, n_total, D.world)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD + ", %.3g h synthetic PCM batch per GPU "
-                               "(%d frames); inputs (%.2f GB) larger than L2" % (args.hours, n_frames, pcm_bytes / 1e9),
-                   "frames_per_gpu": n_frames, "x_realtime_per_gpu": value / world, "host_affinity_rank0": numa},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "clocks": sampler.summary() if sampler else None,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "parity_check": {"frames": chk_n, "byte_identical_to_oracle": parity_frames_equal},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "dropin": dropin, "parity_check": parity,
+        "x_realtime_per_gpu": value / D.world, "host_affinity_rank0": D.numa,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# --config D: the 18-service ensemble, sharded by service and time
+# ------------------------------------------------------------------------------------------------------------------
+def run_ensemble(args):
+    import numpy as np
+    import torch
+    import odr_audioenc_b200 as tl
+    from odr_audioenc_b200 import sharding
+
+    D = Dist()
+    L = tl.lib()
+    fs = 48000
+    n_frames = int(round(args.hours * 3600 * fs / 1152))
+    services = [(f, 1 if m == "m" else 2, br, n_frames) for f, m, br in ENSEMBLE]
+    plan = sharding.ensemble_shards(services, D.world)
+    mine = plan[D.rank]
+    encs, work = {}, []
+    for p in mine:
+        f, mode, br = ENSEMBLE[p.service]
+        if (f, mode, br) not in encs:
+            encs[(f, mode, br)] = tl.BatchEncoder(f, mode, br, 1, 0, D.local, args.chunk_frames or 148 * 256)
+        e = encs[(f, mode, br)]
+        first, end = sharding.pcm_slice(p)
+        d_pcm = synth_pcm(first, end, e.nch, f, 5000 + p.service, D.dev)
+        d_out = torch.empty((p.f1 - p.f0) * e.lg_frame, dtype=torch.uint8, device=D.dev)
+        work.append((e, p, d_pcm, d_out))
+
+    def sync_all():
+        for e in encs.values():
+            e.sync()
+
+    def step_device():
+        for e, p, d_pcm, d_out in work:
+            e.encode_device(d_pcm.data_ptr() + p.history_samples * e.nch * 2, p.f1 - p.f0, p.history_samples, p.has_next,
+                            None, d_out.data_ptr())
+
+    h_bufs = []
+    for e, p, d_pcm, d_out in work:
+        h_pcm = pinned_array(L, d_pcm.numel() * 2, np.int16, (-1, e.nch))
+        h_out = pinned_array(L, d_out.numel(), np.uint8, (-1,))
+        torch.from_numpy(h_pcm).copy_(d_pcm)
+        h_bufs.append((h_pcm, h_out))
+    torch.cuda.synchronize()
+
+    def step_host():
+        for (e, p, _, _), (h_pcm, h_out) in zip(work, h_bufs):
+            e.encode_async(h_pcm, p.f1 - p.f0, p.history_samples, p.has_next, h_out)
+
+    sampler = ClockSampler(D.local) if D.rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = sum(e.launches for e in encs.values())
+    _, t_dev = timed(D, step_device, sync_all, args.steps, args.warmup)   # several encoders / streams: wall clock
+    launches = (sum(e.launches for e in encs.values()) - launches0) // (args.steps + args.warmup)
+    if sampler:
+        sampler.stop()
+    _, t_host = timed(D, step_host, sync_all, args.steps, args.warmup)
+    same = all(bool(torch.equal(torch.from_numpy(h_out).to(D.dev), d_out)) for (_, _, _, d_out), (_, h_out) in zip(work, h_bufs))
+    host_same = D.allmin(1.0 if same else 0.0) == 1.0
+
+    # ---- concatenation parity: rank 0 encodes every service whole on its GPU and compares each piece with it
+    import torch.distributed as dist
+    ok, compared = True, 0
+    for owner in range(D.world):
+        for p in plan[owner]:
+            f, mode, br = ENSEMBLE[p.service]
+            nbytes = (p.f1 - p.f0) * 3 * br
+            if owner == D.rank:
+                piece = next(d_out for (_, q, _, d_out) in work if q is p)
+            if owner != 0:
+                if D.rank == owner:
+                    dist.send(piece, dst=0)
+                elif D.rank == 0:
+                    piece = torch.empty(nbytes, dtype=torch.uint8, device=D.dev)
+                    dist.recv(piece, src=owner)
+            if D.rank == 0:
+                nch = 1 if mode == "m" else 2
+                e = encs.get((f, mode, br)) or tl.BatchEncoder(f, mode, br, 1, 0, D.local, 148 * 256)
+                encs[(f, mode, br)] = e
+                whole_pcm = synth_pcm(0, n_frames * 1152, nch, f, 5000 + p.service, D.dev)
+                whole = torch.empty(n_frames * 3 * br, dtype=torch.uint8, device=D.dev)
+                e.encode_device(whole_pcm.data_ptr(), n_frames, 0, False, None, whole.data_ptr())
+                e.sync()
+                ok = ok and bool(torch.equal(piece, whole[p.f0 * 3 * br:p.f1 * 3 * br]))
+                compared += nbytes
+                del whole_pcm, whole
+    if D.rank == 0:
+        audio = len(ENSEMBLE) * n_frames * 1152 / fs
+        cost = sharding.plan_cost(plan, services)
+        print(json.dumps({
+            "metric": METRIC, "value": audio * args.steps / t_dev, "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "DAB ensemble: 18 MP2 services x %.3g h, 6x192 4x160 4x128 2x112 kbit/s joint stereo + 2x96 mono, "
+                                   "psy model 1, sharded by service and time (ensemble_shards) over %d GPU(s)" % (args.hours, D.world),
+                       "pieces_per_rank": [len(p) for p in plan], "load_imbalance": max(cost) / (sum(cost) / D.world)},
+            "e2e": {"value": audio * args.steps / t_host, "unit": UNIT,
+                    "h2d_bytes_per_step": sum(int(n_frames * 1152 * (1 if m == "m" else 2) * 2) for _, m, _ in ENSEMBLE),
+                    "d2h_bytes_per_step": sum(int(n_frames * 3 * br) for _, _, br in ENSEMBLE),
+                    "host_equals_device_output": host_same},
+            "gpu_launches": int(launches * args.steps), "clocks": sampler.summary() if sampler else None,
+            "parity_check": {"concatenation_equals_single_gpu": ok, "concatenation_bytes": compared,
+                             "what": "every piece of every service, gathered on rank 0, against rank 0's encode of the whole service"}}))
+    D.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hours", type=float, default=None, help="audio per GPU per step (BASELINE config: 10 h; --strong: the whole stream; D: per service, 1 h)")
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS) + ["D"], help="B = BASELINE configs[1] (default), C = configs[2], E = configs[4], D = configs[3]")
+    ap.add_argument("--strong", action="store_true", help="one stream time-sharded over the ranks (strong scaling) with concatenation parity")
+    ap.add_argument("--chunk-frames", type=int, default=0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=120.0)
+    ap.add_argument("--parity-windows", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)   # timing rule: at least three warm-up steps
+    if args.config == "D":
+        if args.impl == "reference":
+            raise SystemExit("--config D has no reference arm (use the default config)")
+        args.hours = 1.0 if args.hours is None else args.hours  # BASELINE configs[3]: 1 h per service
+        return run_ensemble(args)
+    args.hours = 10.0 if args.hours is None else args.hours
+    cfg = Cfg(args.config)
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+    return run_stream(args, cfg)
 
 
 if __name__ == "__main__":

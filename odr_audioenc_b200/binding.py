@@ -140,6 +140,14 @@ class BatchEncoder:
                                       int(has_next), xp.ctypes.data if xp is not None else None, out.ctypes.data))
         return out
 
+    def encode_async(self, pcm, n_frames, history, has_next, out, xpad=None):
+        """tlb_batch_encode_async on caller-owned (ideally pinned) arrays: returns once the work is queued; sync() waits.
+        pcm row `history` = first sample to encode."""
+        L = lib()
+        L.tlb_batch_encode_async.argtypes = L.tlb_batch_encode.argtypes
+        _check(L.tlb_batch_encode_async(self._h, pcm.ctypes.data + history * self.nch * 2, n_frames, history, int(has_next),
+                                        xpad.ctypes.data if xpad is not None else None, out.ctypes.data))
+
     def encode_device(self, d_pcm, n_frames, history, has_next, d_xpad, d_out):
         """Raw device pointers (ints); asynchronous on self.stream."""
         _check(lib().tlb_batch_encode_device(self._h, d_pcm, n_frames, history, int(has_next), d_xpad, d_out))

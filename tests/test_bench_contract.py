@@ -23,6 +23,23 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["vs_baseline"] is None and d["unit"] == "audio-s/s"
+    assert "same PCM" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_windows_come_from_the_gpu_arms_stream():
+    """any window of the synthetic stream is reproducible from its absolute sample indices alone"""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    cpu = torch.device("cpu")
+    whole = bench.synth_pcm(0, 50000, 2, 48000, bench.STREAM_SEED, cpu)
+    part = bench.synth_pcm(12345, 23456, 2, 48000, bench.STREAM_SEED, cpu)
+    assert torch.equal(whole[12345:23456], part)
+    assert not torch.equal(part, bench.synth_pcm(12345, 23456, 2, 48000, bench.STREAM_SEED + 1, cpu))
+    cfg = bench.Cfg("B")
+    wins = bench.reference_windows(cfg, 1500000, 16, 120.0)
+    assert len(wins) == 16 and wins[0] == (0, 5000) and wins[-1][0] + wins[-1][1] <= 1500000
+    assert cfg.flops_per_frame == 212132 + 2304 and cfg.bytes_per_frame == 5184
 
 
 @pytest.mark.gpu
@@ -32,7 +49,9 @@ def test_b200_arm_line():
     assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     r = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernels"} <= set(r)
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["bound"] in ("hbm", "tensor")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["bound"] == "fp64" and r["unit"] == "TFLOP/s"
+    assert abs(r["hbm"]["frac"] - r["hbm"]["achieved"] / r["hbm"]["peak"]) < 1e-9 and 0 < r["path"]["frac"] < 1
+    assert d["e2e"]["copy_ceiling"]["value"] > 0 and d["dropin"]["us_per_frame"] > 0
     assert abs(sum(k["share"] for k in r["kernels"].values()) - 1.0) < 1e-6
     assert d["parity_check"]["byte_identical_to_oracle"] == d["parity_check"]["frames"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])

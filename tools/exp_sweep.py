@@ -17,7 +17,7 @@ for spec in sys.argv[1:]:
     extra = parts[2:]  # further bench.py flags, e.g. --config=E
     env = dict(os.environ, TLB_EXP=exp)
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--no-cpu-baseline", "--no-e2e", "--steps", "4", "--warmup", "3",
-           "--chunk-frames", str(chunk)] + extra
+           "--chunk-frames", str(chunk), "--no-dropin"] + extra
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if not line:
