@@ -152,7 +152,8 @@ TLB_API void tlb_host_free(void *p);
 /* Per-frame intermediate results of the most recent chunk (parity tests read these; layouts below).
  * Copies min(bytes, available) bytes and returns the number copied, or a negative error. */
 enum {
-    TLB_TAP_SB_SAMPLE = 0,  /* double [frames][nch][36][32]  subband samples (subband.c:201-310) */
+    TLB_TAP_SB_SAMPLE = 0,  /* double [frames][nch][36][32]  subband samples (subband.c:201-310); subbands >= sblimit,
+                             * which the reference computes but never reads, are not kept and read as 0 */
     TLB_TAP_SCALAR_PRE = 1, /* uint8  [frames][2][3][32]     scalefactor indices before the scfsi pattern */
     TLB_TAP_J_SCALE = 2,    /* uint8  [frames][3][32]        joint-stereo scalefactor indices */
     TLB_TAP_SMR = 3,        /* double [frames][2][32]        signal-to-mask ratios (psycho_1.c:568-581) */
@@ -168,6 +169,12 @@ typedef struct {
     uint32_t crc16;            /* crc.c:12-41 */
 } tlb_side;
 TLB_API long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes);
+
+/* State of the libtoolame-dab drop-in stream (include/toolame.h): 0 while it is healthy, otherwise the TLB_E_* code
+ * that stopped it.  The reference's API has no error return on toolame_encode_frame (it returns bytes written), so a
+ * batch that cannot be encoded -- after one retry on a fresh encoder -- stops the stream instead of leaving a gap
+ * in it: every later call returns 0 bytes, toolame_finish hands out what was complete, toolame_init starts again. */
+TLB_API int toolame_b200_status(void);
 
 #ifdef __cplusplus
 }

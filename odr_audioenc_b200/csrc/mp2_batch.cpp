@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mp2_device.h"
+#include "tlb_internal.h"
 
 #define MP2_TABLE_QUAL [[maybe_unused]] static const
 #include "mp2_alloc_tables.h"
@@ -90,6 +91,7 @@ int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
         else P.tablenum = 3;
     } else P.tablenum = 4;
     P.sblimit = MP2_TAB_SBLIMIT[P.tablenum];
+    P.sbw = P.sblimit <= 8 ? 8 : P.sblimit <= 16 ? 16 : 32; // whole 64-byte pieces: rows that are not cut slow the stores down
     {   // ref: availbits.c:42-46; the padding branch (non-integral slot count) only exists at 44.1 / 22.05 kHz
         static const double s_freq[2][3] = {{22.05, 24, 16}, {44.1, 48, 32}};
         const double average = (1152.0 / s_freq[P.version][P.sfreq_idx]) * ((double)kbps / 8.0);
@@ -174,7 +176,7 @@ int alloc_slot(tlb_batch *b, Slot &s, size_t frames)
     CU(cudaMalloc(&s.d_pcm, (HALO + fa * 1152) * nch * sizeof(int16_t)));
     CU(cudaMalloc(&s.d_xpad, fa * (size_t)(b->P.pad_len + 1)));
     CU(cudaMalloc(&s.d_out, frames * (size_t)b->P.lg_frame));
-    CU(cudaMalloc(&s.sb, fa * nch * 1152 * sizeof(double)));
+    CU(cudaMalloc(&s.sb, fa * nch * 36 * (size_t)b->P.sbw * sizeof(double)));
     const size_t fa32 = (fa + 31) / 32 * 32; // frame-tile layouts are padded to whole tiles of 32 frames
     CU(cudaMalloc(&s.scalar_pre, fa32 * 192));
     CU(cudaMalloc(&s.j_scale, fa * 96));
@@ -243,6 +245,8 @@ int check_args(const tlb_batch *b, const void *pcm, size_t history, const void *
 }
 
 } // namespace
+
+int tlb_fail(int code, const char *msg) { return fail(code, msg); }
 
 extern "C" {
 
@@ -578,7 +582,7 @@ long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes)
     const void *src = nullptr;
     size_t avail = 0;
     switch (what) {
-    case TLB_TAP_SB_SAMPLE: src = s.sb; avail = fa * (size_t)b->P.nch * 1152 * sizeof(double); break;
+    case TLB_TAP_SB_SAMPLE: src = s.sb; avail = fa * (size_t)b->P.nch * 1152 * sizeof(double); break; // (expanded below)
     case TLB_TAP_SCALAR_PRE: src = s.scalar_pre; avail = fa * 192; break;
     case TLB_TAP_J_SCALE: src = s.j_scale; avail = fa * 96; break;
     case TLB_TAP_SMR: src = s.smr; avail = fa * 64 * sizeof(double); break;
@@ -586,6 +590,16 @@ long tlb_batch_tap(tlb_batch *b, int what, void *dst, size_t bytes)
     default: return fail(TLB_E_ARG, "unknown tap");
     }
     const size_t n = std::min(avail, bytes);
+    if (what == TLB_TAP_SB_SAMPLE) {
+        // kept on the device as rows of sbw subbands (those below sblimit): hand out rows of 32, zeros above
+        const size_t rows = fa * (size_t)b->P.nch * 36, sbw = (size_t)b->P.sbw;
+        std::vector<double> raw(rows * sbw), lin(rows * 32, 0.0);
+        CU(cudaMemcpy(raw.data(), src, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t r = 0; r < rows; r++)
+            std::memcpy(&lin[r * 32], &raw[r * sbw], (size_t)b->P.sblimit * sizeof(double));
+        std::memcpy(dst, lin.data(), n);
+        return (long)n;
+    }
     if (what == TLB_TAP_SCALAR_PRE || what == TLB_TAP_SMR) {
         // stored on the device in the frame-tile layout [frame/32][field][frame%32]: put frames back in order
         const size_t nf = what == TLB_TAP_SMR ? 64 : 192, esz = what == TLB_TAP_SMR ? sizeof(double) : 1;

@@ -8,6 +8,7 @@
 // Per-stream constants handed to every kernel by value.
 struct Mp2Params {
     int nch, sblimit, tablenum;
+    int sbw;                            // subband samples kept per block row in HBM: 8, 16 or 32 (>= sblimit)
     int mode, mode_ext, jsbound;        // as configured (toolame_set_channel_mode); JS frames re-decide per frame
     int version, bitrate_index, sfreq_idx;
     int dab_ext, lg_frame, pad_len;
@@ -49,7 +50,7 @@ struct Mp2Chunk {
     const int16_t *pcm;     // interleaved s16; element 0 = first sample of the chunk's first frame
     long lo;                // lowest readable sample index relative to pcm (<= 0); below it the signal is 0
     const uint8_t *xpad;    // NULL or records of pad_len+1 bytes, one per analysed frame
-    double *sb;             // [fa][nch][36][32]
+    double *sb;             // [fa][nch][36][sbw]
     uint8_t *scalar_pre;    // [fa][2][3][32]
     uint8_t *j_scale;       // [fa][3][32]
     double *psy_x;          // [ceil(fa*nch/32)][64 chunks][32 items][8 lines]  dB spectrum (psy_line() in mp2_kernels.cu)

@@ -287,7 +287,6 @@ int toolame_finish(unsigned char *output_buffer, size_t output_buffer_size)
     return n;
 }
 
-/* Not part of the reference's API: 0 while the stream is healthy, otherwise the TLB_E_* code that stopped it. */
-TLB_API int toolame_b200_status(void) { return g.error; }
+int toolame_b200_status(void) { return g.error; } // (declared in toolame_b200.h: not part of the reference's API)
 
 } // extern "C"

@@ -1,0 +1,175 @@
+"""CPU: the framing and PAD entry points of include/dab_framing_b200.h -- host-only code.
+
+* ZeroMQ message header against the reference's packed struct (src/Outputs.h:76-92, src/Outputs.cpp:110-127);
+* EDI AF packets against fixtures produced by the reference's own packetiser (tools/make_edi_golden.py ->
+  oracle/_ref/edi_ref_driver = contrib/edioutput/{TagItems,TagPacket,AFPacket}.cpp compiled unmodified), and live
+  against that driver where it is built; plus an independent structural parse (lengths, CRC, counters);
+* the ODR-PadEnc socket protocol (src/PadInterface.cpp:37-150) against a stand-in PadEnc on UNIX datagram sockets."""
+import os
+import socket
+import struct
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import edi_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_zmq_messages_match_the_reference_header_layout():
+    from odr_audioenc_b200 import framing
+    rng = np.random.RandomState(3)
+    for lg in (72, 384, 576, 1728):
+        n = 9
+        frames = rng.randint(0, 256, size=(n, lg)).astype(np.uint8)
+        peaks = rng.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
+        msgs = framing.zmq_messages(frames, lg, peaks)
+        assert msgs.shape == (n, framing.ZMQ_HEADER_SIZE + lg)
+        for f in range(n):
+            # struct zmq_frame_header_t: u16 version = 1, u16 encoder = ZMQ_ENCODER_MPEG_L2 (2), u32 datasize,
+            # i16 audiolevel_left, i16 audiolevel_right; packed, host (little-endian) byte order; data follows
+            want = struct.pack("<HHIhh", 1, 2, lg, int(peaks[f, 0]), int(peaks[f, 1])) + frames[f].tobytes()
+            assert msgs[f].tobytes() == want
+    assert framing.zmq_messages(frames, lg)[0, 8:12].tobytes() == b"\0\0\0\0"   # no peaks given
+
+
+def _crc16_ccitt(data):
+    crc = 0xFFFF
+    for b in data:
+        crc ^= b << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc ^ 0xFFFF
+
+
+def _parse_af(pkt):
+    """ETSI TS 102 821 6.1 / 5.1: returns (seq, [(tag name, value bytes)])"""
+    assert pkt[:2] == b"AF"
+    length, seq, ar, pt = struct.unpack(">IHBc", pkt[2:10])
+    assert ar == 0x90 and pt == b"T" and len(pkt) == 10 + length + 2
+    assert struct.unpack(">H", pkt[-2:])[0] == _crc16_ccitt(pkt[:-2])
+    items, at, body = [], 0, pkt[10:10 + length]
+    while at + 8 <= len(body):
+        name, bits = body[at:at + 4], struct.unpack(">I", body[at + 4:at + 8])[0]
+        assert bits % 8 == 0
+        items.append((name, body[at + 8:at + 8 + bits // 8]))
+        at += 8 + bits // 8
+    assert all(b == 0 for b in body[at:]) and len(body) - at < 8   # alignment padding only
+    return seq, items
+
+
+@pytest.mark.parametrize("name", sorted(edi_cases.CASES))
+def test_edi_packets_equal_the_reference_packetiser(name):
+    from odr_audioenc_b200 import framing
+    case = edi_cases.CASES[name]
+    frames, peaks = edi_cases.inputs(case)
+    g = np.load(os.path.join(GOLD, "edi_%s.npz" % name))
+    ends = np.cumsum(g["sizes"].astype(np.int64))
+    want = [g["data"][e - s:e].tobytes() for s, e in zip(g["sizes"], ends)]
+    e = framing.EdiPacketiser(case["tist"], case["delay_ms"], case["alignment"], case["tai"], case["start"], case["tag"])
+    got = e.packets(frames[:40], case["frame_len"], peaks[:40]) + e.packets(frames[40:], case["frame_len"], peaks[40:])
+    assert len(got) == len(want) == case["n"]
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, "packets differing from the reference packetiser: %s" % bad[:8]
+    # independent structure check: sequence numbers, dsti frame counter modulo 5000, payload, levels
+    for i in (0, 1, case["n"] // 2, case["n"] - 1):
+        seq, items = _parse_af(got[i])
+        names = [n for n, _ in items]
+        assert seq == i % 65536 and names[:4] == [b"*ptr", b"dsti", b"ss\x00\x01", b"ODRa"]
+        assert items[0][1] == b"DSTI\0\0\0\0"
+        hdr = struct.unpack(">H", items[1][1][:2])[0]
+        assert (hdr & 0xFF) + 250 * ((hdr >> 8) & 0x1F) == i % 5000 and bool(hdr & 0x4000) == case["tist"]
+        assert items[2][1] == b"\0\0\0" + frames[i].tobytes()
+        assert items[3][1] == struct.pack(">hh", int(peaks[i, 0]), int(peaks[i, 1]))
+    assert sum(1 for p in got if b"ODRv" in p[-(len(case["tag"]) + 40):]) >= (case["n"] * 24 // 1000) // 10
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "edi_ref_driver")), reason="oracle/_ref/edi_ref_driver not built")
+def test_edi_live_against_the_reference_packetiser():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_edi_golden
+    from odr_audioenc_b200 import framing
+    rng = np.random.RandomState(11)
+    for trial in range(6):
+        case = dict(tist=bool(trial & 1), delay_ms=int(rng.randint(0, 5000)), alignment=[0, 8, 8, 24, 0, 12][trial], tai=37,
+                    start=int(rng.randint(10**9, 2 * 10**9)), tag="t%d" % trial, n=int(rng.randint(50, 700)),
+                    frame_len=int(rng.choice([48, 144, 384, 576, 864])))
+        frames, peaks = edi_cases.inputs(case, seed=trial)
+        want = make_edi_golden.run_ref(case, frames, peaks)
+        e = framing.EdiPacketiser(case["tist"], case["delay_ms"], case["alignment"], case["tai"], case["start"], case["tag"])
+        assert e.packets(frames, case["frame_len"], peaks) == want, case
+
+
+def test_edi_refuses_bad_arguments():
+    from odr_audioenc_b200 import TlbError, framing
+    with pytest.raises(TlbError):
+        framing.EdiPacketiser(tagpacket_alignment=4)
+
+
+class _FakePadEnc(threading.Thread):
+    """stands in for ODR-PadEnc: answers each request [1, padlen] on /tmp/<ident>.padenc with [2] + record"""
+
+    def __init__(self, ident, records):
+        super().__init__(daemon=True)
+        self.path = "/tmp/%s.padenc" % ident
+        self.reply_to = "/tmp/%s.audioenc" % ident
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+        self.sock.bind(self.path)
+        self.sock.settimeout(5.0)
+        self.records, self.requests = list(records), []
+
+    def run(self):
+        try:
+            while self.records:
+                req = self.sock.recv(16)
+                self.requests.append(req)
+                rec = self.records.pop(0)
+                if rec is not None:
+                    self.sock.sendto(b"\x02" + rec, self.reply_to)
+        except socket.timeout:
+            pass
+        finally:
+            self.sock.close()
+            os.unlink(self.path)
+
+
+def test_pad_socket_protocol():
+    import time
+    from odr_audioenc_b200 import TlbError, framing
+    ident = "tlbtest%d" % os.getpid()
+    pad_len = 23
+    rec_a = bytes(range(pad_len - 8)) + b"\xAA" * 8 + bytes([8])          # 8 bytes used
+    rec_b = bytes(pad_len - 2) + b"\x40\x00" + bytes([2])                   # F-PAD only
+    p = framing.PadSocket(ident)
+    used, rec = p.request(pad_len)          # ODR-PadEnc not running: no PAD, zero record (src/PadInterface.cpp:88-99)
+    assert used == 0 and not rec.any()
+    fake = _FakePadEnc(ident, [rec_a, None, rec_b, rec_a[:-3], bytes(pad_len) + b"\x01"])
+    fake.start()
+
+    def request_until_answer():
+        # the reply to request n is normally picked up by request n (same host), at the latest by a later one
+        for _ in range(200):
+            used, rec = p.request(pad_len)
+            if used:
+                return used, rec
+            time.sleep(0.005)
+        raise AssertionError("no PAD reply")
+
+    used, rec = request_until_answer()
+    assert used == 8 and rec.tobytes() == rec_a
+    used, rec = request_until_answer()      # (the request that got no reply returned 0 and was retried)
+    assert used == 2 and rec.tobytes() == rec_b
+    with pytest.raises(TlbError, match="Incorrect PAD length"):
+        request_until_answer()
+    with pytest.raises(TlbError, match="Invalid X-PAD length"):
+        request_until_answer()
+    fake.join(timeout=6)
+    assert fake.requests and all(r == bytes([1, pad_len]) for r in fake.requests)
+    p.close()
+    assert not os.path.exists("/tmp/%s.audioenc" % ident)

@@ -148,8 +148,9 @@ def main():
         emit_array(f, "double", "MP2_DCT", [16, 32], dct, per_line=4)
         f.write("// psy-1 Hann window incl. sqrt(8/3)/1024 normalisation (psycho_1.c:225-233)\n")
         emit_array(f, "double", "MP2_HANN", [1024], hann, per_line=4)
-        f.write("// add_db correction table 10*log10(1+10^(x/10))-x, x=i/10 (psycho_1.c:170-178)\n")
-        emit_array(f, "double", "MP2_DBTABLE", [1000], dbtable, per_line=4)
+        f.write("// add_db correction table 10*log10(1+10^(x/10))-x, x=i/10 (psycho_1.c:170-178); entry 1000 = +0.0 stands in\n"
+                "// for add_db's two early returns (psycho_1.c:189-192) in the branch-free device version\n")
+        emit_array(f, "double", "MP2_DBTABLE", [1001], dbtable + [0.0], per_line=4)
         f.write("// FHT-1024 twiddles (c1,s1,c2,s2) per i for the stages k1=4,16,64,256 (fft.c:1138-1148)\n")
         f.write("#define MP2_FHT_TW_COUNT %d\n" % (len(tw) // 4))
         emit_array(f, "int", "MP2_FHT_TW_OFFSET", [4], tw_off, fmt=str)

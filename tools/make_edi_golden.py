@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/edi_*.npz with the reference's own EDI packetiser (oracle/_ref/edi_ref_driver: the
+unmodified contrib/edioutput sources behind the call sequence of Output::EDI::write_frame).  Build container only."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import edi_cases  # noqa: E402
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "edi_ref_driver")
+
+
+def run_ref(case, frames, peaks):
+    n, frame_len = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        rec = np.zeros((n, frame_len + 4), dtype=np.uint8)
+        rec[:, :frame_len] = frames
+        rec[:, frame_len:] = peaks.astype(np.int16).view(np.uint8).reshape(n, 4)
+        rec.tofile(os.path.join(td, "in.bin"))
+        subprocess.run([DRIVER, str(int(case["tist"])), str(case["delay_ms"]), str(case["alignment"]), str(case["tai"]),
+                        str(case["start"]), case["tag"], str(frame_len), os.path.join(td, "in.bin"), os.path.join(td, "out.bin")],
+                       check=True)
+        raw = open(os.path.join(td, "out.bin"), "rb").read()
+    out, at = [], 0
+    while at < len(raw):
+        size = int(np.frombuffer(raw[at:at + 4], dtype=np.uint32)[0])
+        out.append(raw[at + 4:at + 4 + size])
+        at += 4 + size
+    return out
+
+
+if __name__ == "__main__":
+    for name, case in edi_cases.CASES.items():
+        frames, peaks = edi_cases.inputs(case)
+        pk = run_ref(case, frames, peaks)
+        sizes = np.array([len(p) for p in pk], dtype=np.uint32)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "edi_%s.npz" % name), sizes=sizes,
+                            data=np.frombuffer(b"".join(pk), dtype=np.uint8))
+        print(name, len(pk), "packets", int(sizes.sum()), "bytes")
