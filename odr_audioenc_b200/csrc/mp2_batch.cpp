@@ -21,7 +21,7 @@
 #define MP2_TABLE_QUAL [[maybe_unused]] static const
 #include "mp2_alloc_tables.h"
 #include "mp2_tables.h"
-#include "mp2_psy2_init.h"
+#include "mp2_psy2_tables.h"
 
 namespace {
 
@@ -300,33 +300,36 @@ int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t 
             while (j < P.sub_size && (MP2_LTG_LINE[fq][j] >> 4) == i) j++;
             T.mm_j1[i] = (uint8_t)j;
         }
-        mp2_psy0_init(T.ath_min, (double)cfg->sample_rate); // (FLOAT) s_freq[version][idx] * 1000: toolame.c:365
+        // psy model 0's absolute-threshold minima and psy model 2's start-up tables are frozen per sample rate in
+        // mp2_psy2_tables.h (tools/gen_tables.py reads them back from the compiled reference: psycho_0.c:36-47,
+        // psycho_2.c:259-420): nothing is evaluated with libm here
+        int ri = -1;
+        for (int i = 0; i < MP2_P2_RATES; i++)
+            if (MP2_P2_RATE[i] == cfg->sample_rate) ri = i;
+        if (ri < 0) { tlb_batch_destroy(b); return fail(TLB_E_UNSUPP, "no start-up tables for this sample rate"); }
+        std::memcpy(T.ath_min, MP2_P0_ATH_MIN[ri], sizeof T.ath_min);
         if (cudaMalloc(&b->d_tables, sizeof T) != cudaSuccess ||
             cudaMemcpy(b->d_tables, &T, sizeof T, cudaMemcpyHostToDevice) != cudaSuccess) {
             tlb_batch_destroy(b);
             return fail(TLB_E_CUDA, "table upload failed");
         }
-    }
-    if (P.psy == 2) {
-        // host-side start-up tables, evaluated with libm as the reference does (heap: 33 kB each, and re-entrant)
-        std::unique_ptr<mp2_psy2_tables> Hp(new mp2_psy2_tables);
-        std::unique_ptr<Mp2Psy2Tables> Dp(new Mp2Psy2Tables);
-        mp2_psy2_tables &H = *Hp;
-        Mp2Psy2Tables &D = *Dp;
-        if (mp2_psy2_init(&H, (double)cfg->sample_rate)) { tlb_batch_destroy(b); return fail(TLB_E_PARAM, "psy-2 tables"); }
-        std::memset(&D, 0, sizeof D);
-        for (int j = 0; j < 64; j++)
-            for (int k = 0; k < 64; k++) D.sT[k][j] = H.s[j][k];
-        for (int j = 0; j < 64; j++) {
-            D.tmn[j] = H.tmn[j]; D.rnorm[j] = H.rnorm[j]; D.bmax_of[j] = H.bmax_of[j]; D.numlines[j] = H.numlines[j];
-        }
-        for (int j = 0; j <= 64; j++) D.first_line[j] = H.first_line[j];
-        for (int j = 0; j < 513; j++) D.partition[j] = (uint8_t)H.partition[j];
-        D.absthr_table = H.absthr_table;
-        if (cudaMalloc(&b->d_tables2, sizeof D) != cudaSuccess ||
-            cudaMemcpy(b->d_tables2, &D, sizeof D, cudaMemcpyHostToDevice) != cudaSuccess) {
-            tlb_batch_destroy(b);
-            return fail(TLB_E_CUDA, "psy-2 table upload failed");
+        if (P.psy == 2) {
+            std::unique_ptr<Mp2Psy2Tables> Dp(new Mp2Psy2Tables);
+            Mp2Psy2Tables &D = *Dp;
+            std::memset(&D, 0, sizeof D);
+            std::memcpy(D.sT, MP2_P2_ST[ri], sizeof D.sT);
+            std::memcpy(D.tmn, MP2_P2_TMN[ri], sizeof D.tmn);
+            std::memcpy(D.rnorm, MP2_P2_RNORM[ri], sizeof D.rnorm);
+            std::memcpy(D.bmax_of, MP2_P2_BMAX_OF[ri], sizeof D.bmax_of);
+            std::memcpy(D.numlines, MP2_P2_NUMLINES[ri], sizeof D.numlines);
+            std::memcpy(D.first_line, MP2_P2_FIRST_LINE[ri], sizeof D.first_line);
+            std::memcpy(D.partition, MP2_P2_PARTITION[ri], sizeof D.partition);
+            D.absthr_table = MP2_P2_ABSTHR_TABLE[ri];
+            if (cudaMalloc(&b->d_tables2, sizeof D) != cudaSuccess ||
+                cudaMemcpy(b->d_tables2, &D, sizeof D, cudaMemcpyHostToDevice) != cudaSuccess) {
+                tlb_batch_destroy(b);
+                return fail(TLB_E_CUDA, "psy-2 table upload failed");
+            }
         }
     }
     *out = b;

@@ -26,7 +26,7 @@ struct Mp2PsyTables {
     double ath_min[32];  // psy model 0: lowest absolute threshold per subband in dB (psycho_0.c:36-47)
 };
 
-// Start-up tables of psychoacoustic model 2 (host-computed: mp2_psy2_init.h), device copy.
+// Start-up tables of psychoacoustic model 2 (frozen per sample rate in mp2_psy2_tables.h), device copy.
 struct Mp2Psy2Tables {
     double sT[64][64];    // spreading function transposed: sT[k][j] = s[j][k], partition k into partition j
     double tmn[64], rnorm[64], bmax_of[64];

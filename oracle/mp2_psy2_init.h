@@ -1,6 +1,7 @@
-// mp2_psy2_init.h -- start-up tables of psychoacoustic model 2, evaluated on the HOST with libm exactly as the
-// reference does in psycho_2_init (ref: psycho_2.c:259-420).  Plain C, shared by the product's host code
-// (mp2_batch.cpp uploads the result to the device) and by the test oracle.
+// mp2_psy2_init.h -- TEST INFRASTRUCTURE (part of the oracle): start-up tables of psychoacoustic model 2 and of
+// model 0, evaluated with libm exactly as the reference does in psycho_2_init (ref: psycho_2.c:259-420) and
+// psycho_0 (ref: psycho_0.c:36-47, ath.c:7-49).  The product does not compute these: it carries them frozen from the
+// compiled reference (csrc/mp2_psy2_tables.h); tests/test_tables.py checks that both hold the same bits.
 #pragma once
 #include <math.h>
 #include <string.h>

@@ -184,6 +184,59 @@ def main():
         emit_array(f, "double", "MP2_P2_WINDOW", [1024], window2, per_line=4)
         f.write("// absolute threshold per FFT line for 32/16, 44.1/22.05 and 48/24 kHz (absthr.h)\n")
         emit_array(f, "double", "MP2_ABSTHR", [3, 513], absthr, per_line=6)
+        # ---- start-up tables of psycho_2_init (psycho_2.c:259-420), read back from the reference itself after it
+        # has run for each sample rate the encoder accepts (oracle/psy2_tap.c), and psy model 0's lowest absolute
+        # threshold per subband (psycho_0.c:36-47) from the reference's ATH_dB (ath.c:7-49)
+        tap = C.CDLL(os.path.join(os.path.dirname(REF), "libpsy2_tap.so"))
+        tap.psy2_tap_init.argtypes = [C.c_double]
+        for fn, ct in (("partition", C.c_int), ("numlines", C.c_int), ("cbval", C.c_double), ("rnorm", C.c_double),
+                       ("tmn", C.c_double), ("s", C.c_double), ("bmax", C.c_double), ("absthr", C.c_double)):
+            getattr(tap, "psy2_tap_" + fn).restype = C.POINTER(ct)
+        lib.ATH_dB.restype = C.c_double
+        lib.ATH_dB.argtypes = [C.c_double, C.c_double]
+        rates = [48000, 24000, 32000, 16000]
+        part, numl, first, tmn, rnorm, bmax_of, s_t, abs_idx, ath_min = [], [], [], [], [], [], [], [], []
+        for fs in rates:
+            tap.psy2_tap_init(float(fs))
+            p_ = [tap.psy2_tap_partition()[i] for i in range(513)]
+            n_ = [tap.psy2_tap_numlines()[i] for i in range(64)]
+            cb_ = [tap.psy2_tap_cbval()[i] for i in range(64)]
+            s_ = [tap.psy2_tap_s()[i] for i in range(64 * 64)]
+            bm = [tap.psy2_tap_bmax()[i] for i in range(27)]
+            n_part = p_[512] + 1
+            assert sum(n_[:n_part]) == 513 and all(b >= a for a, b in zip(p_, p_[1:]))
+            fl = [p_.index(j) for j in range(n_part)] + [513] * (65 - n_part)   # partitions are runs of consecutive lines
+            picked = [tap.psy2_tap_absthr()[i] for i in range(513)]
+            abs_idx.append([absthr[513 * t:513 * (t + 1)] for t in range(3)].index(picked))
+            part += p_ + [0] * 7
+            numl += n_
+            first += fl
+            tmn += [tap.psy2_tap_tmn()[i] for i in range(64)]
+            rnorm += [tap.psy2_tap_rnorm()[i] for i in range(64)]
+            bmax_of += [bm[int(c + 0.5)] for c in cb_]            # psycho_2.c:195-196: bmax[(unsigned int)(cbval[j] + 0.5)]
+            s_t += [s_[j * 64 + k] for k in range(64) for j in range(64)]   # transposed: sT[k][j] = s[j][k]
+            am = [1000.0] * 32                                      # psycho_0.c:36-47
+            for i in range(512):
+                v = lib.ATH_dB(i * (float(fs) / 1024.0), 0.0)
+                if v < am[i >> 4]:
+                    am[i >> 4] = v
+            ath_min += am
+        f.write("// ---- per sample rate: the start-up tables psycho_2_init builds with libm (psycho_2.c:259-420), read back from\n"
+                "// the compiled reference (oracle/psy2_tap.c); sT is the spreading function transposed, sT[k][j] = s[j][k]\n")
+        f.write("// (host side only: the kernels get them through Mp2Psy2Tables / Mp2PsyTables)\n#ifndef MP2_DEVICE_TABLES_ONLY\n")
+        f.write("#define MP2_P2_RATES %d\n" % len(rates))
+        emit_array(f, "int", "MP2_P2_RATE", [len(rates)], rates, fmt=str)
+        emit_array(f, "int", "MP2_P2_ABSTHR_TABLE", [len(rates)], abs_idx, fmt=str)
+        emit_array(f, "unsigned char", "MP2_P2_PARTITION", [len(rates), 520], part, per_line=26, fmt=str)
+        emit_array(f, "int", "MP2_P2_NUMLINES", [len(rates), 64], numl, per_line=16, fmt=str)
+        emit_array(f, "int", "MP2_P2_FIRST_LINE", [len(rates), 65], first, per_line=13, fmt=str)
+        emit_array(f, "double", "MP2_P2_TMN", [len(rates), 64], tmn, per_line=4)
+        emit_array(f, "double", "MP2_P2_RNORM", [len(rates), 64], rnorm, per_line=4)
+        emit_array(f, "double", "MP2_P2_BMAX_OF", [len(rates), 64], bmax_of, per_line=8)
+        emit_array(f, "double", "MP2_P2_ST", [len(rates), 64, 64], s_t, per_line=4)
+        f.write("// psy model 0: lowest absolute threshold of hearing per subband in dB (psycho_0.c:36-47 over ath.c:7-49)\n")
+        emit_array(f, "double", "MP2_P0_ATH_MIN", [len(rates), 32], ath_min, per_line=4)
+        f.write("#endif\n")
     print("wrote", out2, os.path.getsize(out2), "bytes")
 
 
