@@ -9,6 +9,10 @@
 //              File output :55-62 of src/Outputs.cpp.  Like odr-audioenc it never emits the last frame(s) still held
 //              in the re-framer / the encoder's bit buffer at end of file.
 //   (default)  the batch path: the whole file in one tlb_batch_encode call; every frame is written.
+//   --edi F / --zmq F   (batch mode) also write what the EDI / ZeroMQ outputs of odr-audioenc would put on the wire for
+//              these frames: the AF packets of Output::EDI::write_frame (src/Outputs.cpp:194-263) back to back, and the
+//              ZeroMQ messages of Output::ZMQ::write_frame (src/Outputs.cpp:101-141), with the per-frame peak levels
+//              (tlb_edi_packets / tlb_zmq_messages, include/dab_framing_b200.h).
 //
 // WAV parsing follows src/wavfile.cpp:74-182 (RIFF chunks, 'fmt ' incl. WAVE_FORMAT_EXTENSIBLE, 'data'); only
 // 16-bit PCM is accepted (src/FileInput.cpp:60-75).  Gain (-g dB) and peak levels are done on the GPU in batch mode
@@ -22,6 +26,7 @@
 #include <string>
 #include <vector>
 
+#include "../include/dab_framing_b200.h"
 #include "../include/toolame.h"
 #include "../include/toolame_b200.h"
 
@@ -57,7 +62,7 @@ static bool read_wav(const char *path, std::vector<int16_t> &pcm, int &channels,
 
 int main(int argc, char **argv)
 {
-    const char *in = nullptr, *out = nullptr;
+    const char *in = nullptr, *out = nullptr, *edi_path = nullptr, *zmq_path = nullptr;
     int bitrate = 192, rate = 48000, channels = 2, psy = 1, raw = 0, stream = 0;
     double gain_db = 0;
     std::string mode;
@@ -74,7 +79,9 @@ int main(int argc, char **argv)
         else if (a == "--dabpsy") psy = std::atoi(val());
         else if (a == "--raw") raw = 1;
         else if (a == "--stream") stream = 1;
-        else { std::fprintf(stderr, "usage: dabenc -i IN.wav -o OUT.mp2 [-b kbps] [-r Hz -c ch --raw] [-g dB] [--dabmode s|d|j|m] [--dabpsy 1|2] [--stream]\n"); return 2; }
+        else if (a == "--edi") edi_path = val();
+        else if (a == "--zmq") zmq_path = val();
+        else { std::fprintf(stderr, "usage: dabenc -i IN.wav -o OUT.mp2 [-b kbps] [-r Hz -c ch --raw] [-g dB] [--dabmode s|d|j|m] [--dabpsy 0|1|2] [--stream] [--edi OUT.edi] [--zmq OUT.zmq]\n"); return 2; }
     }
     if (!in || !out) { std::fprintf(stderr, "dabenc: -i and -o are required\n"); return 2; }
     std::vector<int16_t> pcm;
@@ -145,6 +152,29 @@ int main(int argc, char **argv)
         for (size_t f = 0; f < n_frames; f++) {
             peak_l = std::max<int>(peak_l, peaks[2 * f]);
             peak_r = std::max<int>(peak_r, peaks[2 * f + 1]);
+        }
+        // DAB frames are 24 ms = 3 * bitrate bytes (src/odr-audioenc.cpp:1211); at 48 kHz that is the MPEG frame, at
+        // 24 kHz half of one (the level pair of an MPEG frame then goes with both halves)
+        const size_t dab_len = 3 * (size_t)bitrate, n_dab = mp2.size() / dab_len, per = (size_t)info.lg_frame / dab_len;
+        std::vector<int16_t> dab_peaks(2 * n_dab + 2);
+        for (size_t d = 0; d < n_dab; d++) { dab_peaks[2 * d] = peaks[2 * (d / per)]; dab_peaks[2 * d + 1] = peaks[2 * (d / per) + 1]; }
+        if (zmq_path) {
+            std::vector<uint8_t> msgs(n_dab * (TLB_ZMQ_HEADER_SIZE + dab_len));
+            const long n = tlb_zmq_messages(mp2.data(), n_dab, dab_len, dab_peaks.data(), msgs.data());
+            FILE *fz = std::fopen(zmq_path, "wb");
+            if (n < 0 || !fz || std::fwrite(msgs.data(), 1, (size_t)n, fz) != (size_t)n) { std::fprintf(stderr, "dabenc: --zmq failed\n"); return 1; }
+            std::fclose(fz);
+        }
+        if (edi_path) {
+            tlb_edi_config ec = {0, 0, 0, 37, 1, "dabenc (libtoolame_b200)"}; // no time stamp, fixed start second: reproducible
+            tlb_edi *edi = nullptr;
+            if (tlb_edi_create(&edi, &ec)) { std::fprintf(stderr, "dabenc: %s\n", tlb_last_error()); return 1; }
+            std::vector<uint8_t> pk(n_dab * tlb_edi_packet_bound(edi, dab_len));
+            const long n = tlb_edi_packets(edi, mp2.data(), n_dab, dab_len, dab_peaks.data(), pk.data(), pk.size(), nullptr);
+            FILE *fe = std::fopen(edi_path, "wb");
+            if (n < 0 || !fe || std::fwrite(pk.data(), 1, (size_t)n, fe) != (size_t)n) { std::fprintf(stderr, "dabenc: --edi failed\n"); return 1; }
+            std::fclose(fe);
+            tlb_edi_destroy(edi);
         }
         tlb_batch_destroy(enc);
     }

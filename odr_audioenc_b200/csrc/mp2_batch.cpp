@@ -119,7 +119,7 @@ struct Slot {
     double *smr = nullptr, *psy_x = nullptr, *psy_w = nullptr, *spike = nullptr;
     unsigned *psy_cand = nullptr, *psy_t0 = nullptr;
     Mp2Maskers *maskers = nullptr;
-    double *p2_energy = nullptr, *p2_phi = nullptr, *p2_r = nullptr;
+    double *p2_energy = nullptr, *p2_cu = nullptr, *p2_su = nullptr, *p2_r = nullptr;
     int16_t *d_peaks = nullptr; // [fa + 1][2]
     tlb_side *side = nullptr;
     cudaStream_t stream = nullptr;
@@ -184,7 +184,8 @@ int alloc_slot(tlb_batch *b, Slot &s, size_t frames)
     const size_t items = fa * nch, tiles = (items + 31) / 32;
     if (b->P.psy == 2) {
         CU(cudaMalloc(&s.p2_energy, (2 * fa + 2) * nch * 520 * sizeof(double)));
-        CU(cudaMalloc(&s.p2_phi, (2 * fa + 2) * nch * 520 * sizeof(double)));
+        CU(cudaMalloc(&s.p2_cu, (2 * fa + 2) * nch * 520 * sizeof(double)));
+        CU(cudaMalloc(&s.p2_su, (2 * fa + 2) * nch * 520 * sizeof(double)));
         CU(cudaMalloc(&s.p2_r, (2 * fa + 2) * nch * 520 * sizeof(double)));
     } else {
         CU(cudaMalloc(&s.psy_x, tiles * 512 * 32 * sizeof(double)));
@@ -209,7 +210,7 @@ void free_buffers(Slot &s)
     cudaFree(s.d_pcm); cudaFree(s.d_xpad); cudaFree(s.d_out); cudaFree(s.sb); cudaFree(s.scalar_pre);
     cudaFree(s.j_scale); cudaFree(s.smr); cudaFree(s.side);
     cudaFree(s.psy_x); cudaFree(s.psy_w); cudaFree(s.psy_cand); cudaFree(s.psy_t0); cudaFree(s.spike); cudaFree(s.maskers);
-    cudaFree(s.p2_energy); cudaFree(s.p2_phi); cudaFree(s.p2_r); cudaFree(s.d_peaks);
+    cudaFree(s.p2_energy); cudaFree(s.p2_cu); cudaFree(s.p2_su); cudaFree(s.p2_r); cudaFree(s.d_peaks);
     s = Slot();
     s.stream = stream;
     s.done = done;
@@ -230,7 +231,7 @@ Mp2Chunk chunk_of(const tlb_batch *b, const Slot &s, const int16_t *pcm, long lo
     Mp2Chunk c;
     c.pcm = pcm; c.lo = lo; c.xpad = xpad; c.sb = s.sb; c.scalar_pre = s.scalar_pre; c.j_scale = s.j_scale;
     c.smr = s.smr; c.side = s.side; c.psy_x = s.psy_x; c.psy_w = s.psy_w; c.psy_cand = s.psy_cand; c.psy_t0 = s.psy_t0;
-    c.spike = s.spike; c.maskers = s.maskers; c.p2_energy = s.p2_energy; c.p2_phi = s.p2_phi; c.p2_r = s.p2_r;
+    c.spike = s.spike; c.maskers = s.maskers; c.p2_energy = s.p2_energy; c.p2_cu = s.p2_cu; c.p2_su = s.p2_su; c.p2_r = s.p2_r;
     c.p2_first_block = lo == 0 ? 0 : -2; // at the stream start the blocks before the first frame are the zero state
     c.out = out; c.fa = fa; c.n_out = n_out;
     return c;

@@ -60,7 +60,7 @@ struct Mp2Chunk {
     double *spike;          // [fa*nch][32]
     Mp2Maskers *maskers;    // [fa*nch]
     double *p2_energy;      // psy-2: [(2*fa+2)*nch][520] energy per block and channel, record (block+2)*nch+ch
-    double *p2_phi;         // psy-2: same layout, phase
+    double *p2_cu, *p2_su;  // psy-2: same layout, cosine and sine of the line's phase
     double *p2_r;           // psy-2: same layout, sqrt(energy)
     long p2_first_block;    // psy-2: lowest block (relative to the chunk's first frame) that exists; earlier = zero state
     double *smr;            // [ceil(fa/32)][64][32] frame-tile layout

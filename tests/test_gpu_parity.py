@@ -308,8 +308,16 @@ def test_example_cli_stream_and_batch_modes(tmp_path):
         f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 2, fs, fs * 4, 4, 16)
                 + b"data" + struct.pack("<I", len(data)) + data)
     ref, _ = oracle.encode(oracle.configure(fs, "j", br), pcm)
-    subprocess.run([exe, "-i", str(wav), "-o", str(tmp_path / "b.mp2"), "-b", str(br)], check=True)
+    subprocess.run([exe, "-i", str(wav), "-o", str(tmp_path / "b.mp2"), "-b", str(br), "--edi", str(tmp_path / "b.edi"),
+                    "--zmq", str(tmp_path / "b.zmq")], check=True)
     assert np.array_equal(np.fromfile(tmp_path / "b.mp2", dtype=np.uint8), ref)
+    # the frames as the ZeroMQ / EDI outputs would send them (include/dab_framing_b200.h), with the GPU's peak levels
+    from odr_audioenc_b200 import framing
+    peaks = np.stack([pcm.reshape(n, 1152, 2)[:, :, c].max(axis=1).clip(min=0) for c in range(2)], axis=1).astype(np.int16)
+    want_zmq = framing.zmq_messages(ref, lg_b := 3 * br, peaks).tobytes()
+    assert (tmp_path / "b.zmq").read_bytes() == want_zmq
+    e = framing.EdiPacketiser(False, 0, 0, 37, 1, "dabenc (libtoolame_b200)")
+    assert (tmp_path / "b.edi").read_bytes() == b"".join(e.packets(ref, lg_b, peaks))
     subprocess.run([exe, "-i", str(wav), "-o", str(tmp_path / "s.mp2"), "-b", str(br), "--stream"], check=True)
     got = np.fromfile(tmp_path / "s.mp2", dtype=np.uint8)
     lg = 3 * br
