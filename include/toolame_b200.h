@@ -98,15 +98,20 @@ TLB_API int tlb_batch_encode(tlb_batch *b, const int16_t *pcm, size_t n_frames, 
 TLB_API int tlb_batch_encode_async(tlb_batch *b, const int16_t *pcm, size_t n_frames, size_t history_samples,
                            int has_next, const uint8_t *xpad, uint8_t *out);
 
-/* Many services (streams) at once, each a whole stream from its start: the multi-service form of the loop in
- * src/odr-audioenc.cpp:819-1276 run once per service.  Services of different configurations run side by side on
- * the GPU.  xpad may be NULL per service; out receives n_frames * lg_frame bytes per service. */
+/* Many services (streams) at once: the multi-service form of the loop in src/odr-audioenc.cpp:819-1276 run once per
+ * service.  Services of different configurations run side by side on the GPU.  An entry is a whole stream from its
+ * start (history_samples = 0, has_next = 0) or a time piece of one (as tlb_batch_encode: pcm[0] = first sample of the
+ * piece's first frame, history_samples valid samples before it, has_next = one more frame follows in pcm) -- what a
+ * rank of a multi-GPU feeder is handed by a plan like odr_audioenc_b200/sharding.py's ensemble_shards.
+ * xpad may be NULL per service; out receives n_frames * lg_frame bytes per service. */
 typedef struct {
     tlb_config cfg;
-    const int16_t *pcm;   /* interleaved s16, n_frames * 1152 * nch samples */
+    const int16_t *pcm;   /* interleaved s16, (n_frames + has_next) * 1152 * nch samples from pcm[0] on */
     size_t n_frames;
-    const uint8_t *xpad;  /* NULL or n_frames records of pad_len + 1 bytes */
+    const uint8_t *xpad;  /* NULL or n_frames + has_next records of pad_len + 1 bytes */
     uint8_t *out;
+    size_t history_samples;
+    int32_t has_next;
 } tlb_service;
 TLB_API int tlb_encode_services(const tlb_service *sv, size_t n, int device, size_t chunk_frames);
 

@@ -76,19 +76,23 @@ def _check(rc):
 
 
 class _Service(C.Structure):
-    _fields_ = [("cfg", _Config), ("pcm", C.c_void_p), ("n_frames", C.c_size_t), ("xpad", C.c_void_p), ("out", C.c_void_p)]
+    _fields_ = [("cfg", _Config), ("pcm", C.c_void_p), ("n_frames", C.c_size_t), ("xpad", C.c_void_p), ("out", C.c_void_p),
+                ("history_samples", C.c_size_t), ("has_next", C.c_int32)]
 
 
 def encode_services(services, device=0, chunk_frames=0):
-    """services: list of dicts(sample_rate, mode, bitrate, psy=1, pad_len=0, pcm=int16 array (samples, nch), xpad=None).
-    Returns the list of encoded streams (uint8 arrays).  tlb_encode_services: one call for a whole ensemble."""
+    """services: list of dicts(sample_rate, mode, bitrate, psy=1, pad_len=0, pcm=int16 array (samples, nch), xpad=None,
+    history=0, has_next=False): whole streams, or time pieces whose pcm starts `history` samples before the piece's
+    first frame and holds one more frame after it when has_next.  Returns the list of encoded streams / pieces
+    (uint8 arrays).  tlb_encode_services: one call for a whole ensemble."""
     n = len(services)
     arr = (_Service * n)()
     keep, outs = [], []
     for i, sv in enumerate(services):
         nch = 1 if sv["mode"] == "m" else 2
         pcm = np.ascontiguousarray(sv["pcm"], dtype=np.int16).reshape(-1, nch)
-        nf = pcm.shape[0] // 1152
+        hist, nxt = int(sv.get("history", 0)), bool(sv.get("has_next", False))
+        nf = (pcm.shape[0] - hist) // 1152 - (1 if nxt else 0)
         cfg = _Config(sv["sample_rate"], ord(sv["mode"]), sv["bitrate"], sv.get("psy", 1), sv.get("pad_len", 0))
         probe = BatchEncoder(sv["sample_rate"], sv["mode"], sv["bitrate"], sv.get("psy", 1), sv.get("pad_len", 0), device, 1)
         out = np.empty(nf * probe.lg_frame, dtype=np.uint8)
@@ -97,7 +101,8 @@ def encode_services(services, device=0, chunk_frames=0):
         xp = np.ascontiguousarray(xp, dtype=np.uint8) if xp is not None else None
         keep += [pcm, xp]
         outs.append(out)
-        arr[i] = _Service(cfg, pcm.ctypes.data, nf, xp.ctypes.data if xp is not None else None, out.ctypes.data)
+        arr[i] = _Service(cfg, pcm.ctypes.data + hist * nch * 2, nf, xp.ctypes.data if xp is not None else None, out.ctypes.data,
+                          hist, int(nxt))
     L = lib()
     L.tlb_encode_services.argtypes = [C.POINTER(_Service), C.c_size_t, C.c_int, C.c_size_t]
     _check(L.tlb_encode_services(arr, n, device, chunk_frames))

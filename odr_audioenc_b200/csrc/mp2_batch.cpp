@@ -444,7 +444,7 @@ int tlb_encode_services(const tlb_service *sv, size_t n, int device, size_t chun
             enc.push_back(b);
             cfgs.push_back(sv[i].cfg);
         }
-        rc = tlb_batch_encode_async(enc[e], sv[i].pcm, sv[i].n_frames, 0, 0, sv[i].xpad, sv[i].out);
+        rc = tlb_batch_encode_async(enc[e], sv[i].pcm, sv[i].n_frames, sv[i].history_samples, sv[i].has_next, sv[i].xpad, sv[i].out);
     }
     for (auto b : enc) {
         const int r2 = tlb_batch_sync(b);

@@ -255,6 +255,36 @@ def test_ensemble_of_services_in_one_call():
         assert np.array_equal(got, want), (s["sample_rate"], s["mode"], s["bitrate"])
 
 
+def test_ensemble_pieces_through_one_call_per_rank():
+    """what a rank of a multi-GPU feeder does: its share of an ensemble_shards plan -- whole services and time pieces
+    with halo and look-ahead frame -- in ONE tlb_encode_services call; the pieces of all ranks reassemble every
+    service byte for byte"""
+    import odr_audioenc_b200 as tl
+    import signals
+    from odr_audioenc_b200 import sharding
+    spec = [(48000, "j", 192, "S1"), (48000, "j", 192, "S8"), (48000, "j", 128, "S2"), (48000, "m", 96, "S1"), (24000, "m", 64, "S8")]
+    n = 90
+    pcms = [signals.make(sig, n, 1 if mode == "m" else 2, fs) for fs, mode, br, sig in spec]
+    services = [(fs, 1 if mode == "m" else 2, br, n) for fs, mode, br, _ in spec]
+    world = 3
+    plan = sharding.ensemble_shards(services, world, min_piece_frames=4)
+    assert sum(len(p) for p in plan) > len(spec)   # at least one service is cut in time
+    got = {i: {} for i in range(len(spec))}
+    for rank in range(world):
+        sv = []
+        for q in plan[rank]:
+            fs, mode, br, _ = spec[q.service]
+            first, end = sharding.pcm_slice(q)
+            sv.append(dict(sample_rate=fs, mode=mode, bitrate=br, pcm=pcms[q.service][first:end], history=q.history_samples,
+                           has_next=q.has_next))
+        for q, out in zip(plan[rank], tl.encode_services(sv, chunk_frames=16)):
+            got[q.service][q.f0] = out
+    for i, (fs, mode, br, _) in enumerate(spec):
+        want, _ = oracle.encode(oracle.configure(fs, mode, br), pcms[i])
+        whole = np.concatenate([got[i][f0] for f0 in sorted(got[i])])
+        assert np.array_equal(whole, want), i
+
+
 def _gain_peak_model(pcm, nch, gain_db):
     """numpy restatement of src/odr-audioenc.cpp:1020-1055 per frame: (left, right) pairs also in mono, truncated
     product wrapped to 16 bits, peaks start at 0"""
@@ -290,6 +320,25 @@ def test_gain_and_peaks_on_device(cfg, gain_db):
     assert np.array_equal(peaks, want_peaks)
     ref, _ = oracle.encode(oracle.configure(fs, mode, br), gained)
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("hist", [481, 1153, 1152, 2305])
+def test_gain_with_odd_history_in_mono(hist):
+    """a mid-stream mono range whose history length is odd: the staged region stays aligned for the gain kernel's
+    sample pairs (one history sample is simply not staged: halo sizes are even) and the frames equal the gained stream"""
+    import ctypes as C
+    import odr_audioenc_b200 as tl
+    n, f0 = 30, 9
+    fs, mode, br, pcm, _, _ = cases.make_case("C", "S8", n)
+    gained, _ = _gain_peak_model(pcm, 1, -4.5)
+    ref, _ = oracle.encode(oracle.configure(fs, mode, br), gained)
+    e = _enc(fs, mode, br, chunk=7)
+    L = tl.lib()
+    L.tlb_batch_set_gain.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    assert L.tlb_batch_set_gain(e._h, -4.5, None) == 0
+    seg = pcm[f0 * 1152 - hist:]
+    got = e.encode(seg, history=hist)
+    assert np.array_equal(got, ref[f0 * e.lg_frame:])
 
 
 def test_example_cli_stream_and_batch_modes(tmp_path):
