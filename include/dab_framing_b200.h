@@ -6,9 +6,11 @@
  *      (src/Outputs.h:76-99) in front of the frame, as Output::ZMQ::write_frame builds it (src/Outputs.cpp:101-141).
  *  (2) EDI: one AF packet (ETSI TS 102 821, 6.1) per frame holding the TAG packet *ptr / dsti / ss1 / ODRa (/ ODRv),
  *      as Output::EDI::write_frame (src/Outputs.cpp:194-263) with contrib/edioutput/TagItems.cpp, TagPacket.cpp and
- *      AFPacket.cpp assembles it, including the frame counter, the 24 ms time stamp arithmetic and the CRC.
- *      The PFT layer (fragmentation + Reed-Solomon, contrib/edioutput/PFT.cpp) and the sockets are not built: the
- *      functions return the packet BYTES; a caller sends them over UDP/TCP (or ZeroMQ) as it likes.
+ *      AFPacket.cpp assembles it, including the frame counter, the 24 ms time stamp arithmetic and the CRC; and the
+ *      PFT layer on top of it (ETSI TS 102 821, 7: fragmentation, optional Reed-Solomon RS(255,207) protection and
+ *      interleaving, PF headers), which the reference always switches on for UDP destinations
+ *      (src/Outputs.cpp:156-165, contrib/edioutput/PFT.cpp).  The sockets are not built: the functions return the
+ *      packet BYTES; a caller sends them over UDP/TCP (or ZeroMQ) as it likes.
  *  (3) PAD ingestion: the ODR-PadEnc request / reply protocol over UNIX datagram sockets
  *      (src/PadInterface.cpp:37-150), delivering records in exactly the layout tlb_batch_encode's `xpad` takes.
  *
@@ -58,6 +60,24 @@ TLB_API long tlb_edi_packet(tlb_edi *e, const uint8_t *frame, size_t len, int16_
 /* A batch: n_frames packets back to back into out; sizes[i] receives the size of packet i. Returns the total. */
 TLB_API long tlb_edi_packets(tlb_edi *e, const uint8_t *frames, size_t n_frames, size_t frame_len, const int16_t *peaks,
                              uint8_t *out, size_t cap, uint32_t *sizes);
+
+/* PFT layer: an AF packet becomes one or more PF fragments (each a datagram).  fec = 0: fragmentation only, payloads of
+ * at most 1400 bytes; fec = m > 0: the packet is cut into chunks of at most chunk_len bytes, each protected by 48
+ * Reed-Solomon bytes (RS(255,207), x^8+x^4+x^3+x^2+1, first root alpha^1), and the protected block is interleaved
+ * over fragments sized so that m lost fragments can be recovered (contrib/edioutput/PFT.cpp:76-231). */
+typedef struct {
+    uint32_t fec;        /* edi::configuration_t::fec (EDI::set_fec) */
+    uint32_t chunk_len;  /* edi::configuration_t::chunk_len; 0 = 207 */
+} tlb_pft_config;
+typedef struct tlb_pft tlb_pft;
+TLB_API int tlb_pft_create(tlb_pft **out, const tlb_pft_config *cfg);
+TLB_API void tlb_pft_destroy(tlb_pft *p);
+/* Upper bounds for one AF packet of af_len bytes: total bytes of all fragments (return value) and their number. */
+TLB_API size_t tlb_pft_bound(const tlb_pft *p, size_t af_len, size_t *max_fragments);
+/* Fragments of the next AF packet of the stream (the PF sequence number counts packets), back to back into out;
+ * sizes[i] receives the size of fragment i (at most max_fragments entries).  Returns the number of fragments. */
+TLB_API long tlb_pft_fragments(tlb_pft *p, const uint8_t *af_packet, size_t af_len, uint8_t *out, size_t cap,
+                               uint32_t *sizes, size_t max_fragments);
 
 /* ---- (3) PAD ingestion ---------------------------------------------------------------------------------- */
 typedef struct tlb_pad tlb_pad;

@@ -65,6 +65,50 @@ struct tlb_edi {
     bool started = false;
 };
 
+// Reed-Solomon RS(255,207) over GF(2^8), field polynomial x^8+x^4+x^3+x^2+1 (0x11d), generator roots alpha^1 ..
+// alpha^48 -- the parameters of contrib/edioutput/PFT.cpp:103-110.  Systematic encoding: the 48 parity bytes are the
+// remainder of data(x) x^48 divided by the generator polynomial, computed with the usual shift register.
+struct Rs255_207 {
+    static constexpr int NROOTS = 48;
+    uint8_t exp[512], log[256], gen[NROOTS + 1]; // gen[] in log form, gen[NROOTS] = 1 (monic)
+    Rs255_207()
+    {
+        unsigned v = 1;
+        for (int i = 0; i < 255; i++) {
+            exp[i] = exp[i + 255] = (uint8_t)v;
+            log[v] = (uint8_t)i;
+            v <<= 1;
+            if (v & 0x100) v ^= 0x11d;
+        }
+        log[0] = 255; // (never used as a logarithm)
+        uint8_t g[NROOTS + 1] = {1}; // coefficients, lowest order first
+        for (int r = 0; r < NROOTS; r++) { // multiply by (x + alpha^(r+1))
+            const int root = r + 1;
+            g[r + 1] = 1;
+            for (int j = r; j > 0; j--) g[j] = (uint8_t)(g[j - 1] ^ (g[j] ? exp[log[g[j]] + root] : 0));
+            g[0] = g[0] ? exp[log[g[0]] + root] : 0;
+        }
+        for (int j = 0; j <= NROOTS; j++) gen[j] = log[g[j]];
+    }
+    void parity(const uint8_t data[207], uint8_t par[NROOTS]) const
+    {
+        std::memset(par, 0, NROOTS);
+        for (int i = 0; i < 207; i++) {
+            const uint8_t fb = (uint8_t)(data[i] ^ par[0]);
+            std::memmove(par, par + 1, NROOTS - 1);
+            par[NROOTS - 1] = 0;
+            if (fb)
+                for (int j = 0; j < NROOTS; j++) par[j] ^= exp[log[fb] + gen[NROOTS - 1 - j]];
+        }
+    }
+};
+
+struct tlb_pft {
+    tlb_pft_config cfg;
+    uint16_t pseq = 0; // PFT::m_pseq
+    std::vector<uint8_t> block;
+};
+
 struct tlb_pad {
     int sock = -1;
     std::string ident;
@@ -224,6 +268,104 @@ long tlb_edi_packets(tlb_edi *e, const uint8_t *frames, size_t n_frames, size_t 
         at += (size_t)n;
     }
     return (long)at;
+}
+
+// ---- PFT (ref: contrib/edioutput/PFT.cpp) -------------------------------------------------------------------------------
+static size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+int tlb_pft_create(tlb_pft **out, const tlb_pft_config *cfg)
+{
+    if (!out || !cfg) return tlb_fail(TLB_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (cfg->chunk_len > 207) return tlb_fail(TLB_E_PARAM, "EDI PFT: maximum chunk size is 207"); // ref: PFT.cpp:59-63
+    tlb_pft *p = new (std::nothrow) tlb_pft();
+    if (!p) return tlb_fail(TLB_E_ARG, "out of memory");
+    p->cfg = *cfg;
+    if (!p->cfg.chunk_len) p->cfg.chunk_len = 207;
+    *out = p;
+    return 0;
+}
+
+void tlb_pft_destroy(tlb_pft *p) { delete p; }
+
+size_t tlb_pft_bound(const tlb_pft *p, size_t af_len, size_t *max_fragments)
+{
+    if (!p || !af_len) return 0;
+    size_t payload = af_len, frags;
+    if (p->cfg.fec) {
+        const size_t c = ceil_div(af_len, p->cfg.chunk_len), k = ceil_div(af_len, c);
+        payload = c * (k + 48);
+        frags = ceil_div(payload, c * 48 / (p->cfg.fec + 1));
+    } else frags = ceil_div(af_len, 1400);
+    if (max_fragments) *max_fragments = frags;
+    return payload + frags * (14 + 2 + 1); // header (12 + RSk/RSz) + CRC, and the rounding of the fragment size
+}
+
+long tlb_pft_fragments(tlb_pft *p, const uint8_t *af, size_t af_len, uint8_t *out, size_t cap, uint32_t *sizes, size_t max_fragments)
+{
+    if (!p || !af || !out || !af_len) return tlb_fail(TLB_E_ARG, "NULL argument");
+    const bool rs = p->cfg.fec > 0;
+    size_t n_frag, frag_size, chunk_len = 0, zero_pad = 0, total;
+    const uint8_t *payload = af;
+    if (rs) {
+        // ref: PFT.cpp:76-137: c = ceil(l / k_max) chunks of k = ceil(l / c) bytes, the last one zero padded; every chunk,
+        // padded to 207 bytes behind its data, gets 48 parity bytes
+        static const Rs255_207 code;
+        const size_t c = ceil_div(af_len, p->cfg.chunk_len);
+        chunk_len = ceil_div(af_len, c);
+        zero_pad = c * chunk_len - af_len;
+        p->block.assign(c * (chunk_len + 48), 0);
+        for (size_t i = 0; i < c; i++) {
+            uint8_t word[207] = {0};
+            const size_t at = i * chunk_len, n = af_len - at < chunk_len ? af_len - at : chunk_len;
+            std::memcpy(word, af + at, n);
+            uint8_t *dst = p->block.data() + i * (chunk_len + 48);
+            std::memcpy(dst, word, chunk_len);
+            code.parity(word, dst + chunk_len);
+        }
+        // ref: PFT.cpp:157-190: s_max = floor(c p / (m + 1)), f = ceil(L / s_max) fragments of ceil(L / f) bytes, byte j of
+        // fragment i = block[j f + i] (interleaved), zero beyond the block
+        total = p->block.size();
+        const size_t s_max = c * 48 / (p->cfg.fec + 1);
+        n_frag = ceil_div(total, s_max);
+        frag_size = ceil_div(total, n_frag);
+        payload = p->block.data();
+    } else { // ref: PFT.cpp:192-222: plain fragmentation, payloads of at most 1400 bytes, the last one may be shorter
+        total = af_len;
+        n_frag = ceil_div(af_len, 1400);
+        frag_size = ceil_div(af_len, n_frag);
+    }
+    if (n_frag > max_fragments && sizes) return tlb_fail(TLB_E_ARG, "PFT: more fragments than sizes[] holds");
+    size_t at = 0;
+    for (size_t i = 0; i < n_frag; i++) {
+        const size_t len = rs ? frag_size : (total - i * frag_size < frag_size ? total - i * frag_size : frag_size);
+        const size_t hdr = 12 + (rs ? 2 : 0) + 2;
+        if (at + hdr + len > cap) return tlb_fail(TLB_E_ARG, "PFT output buffer too small");
+        Writer w(out + at);
+        // ref: PFT.cpp:253-309: PF header = "PF", Pseq, Findex (24 bits), Fcount (24 bits), FEC / Addr flags + Plen,
+        // [RSk, RSz], CRC over the header; the transport header is never used
+        w.u8('P');
+        w.u8('F');
+        w.be16(p->pseq);
+        w.be24((unsigned)i);
+        w.be24((unsigned)n_frag);
+        w.be16((unsigned)len | (rs ? 0x8000u : 0u));
+        if (rs) {
+            w.u8((unsigned)chunk_len);
+            w.u8((unsigned)zero_pad);
+        }
+        w.be16((uint16_t)(crc16_ccitt(0xffff, out + at, w.n) ^ 0xffff));
+        if (rs) {
+            for (size_t j = 0; j < len; j++) {
+                const size_t ix = j * n_frag + i;
+                w.u8(ix < total ? payload[ix] : 0);
+            }
+        } else w.bytes(payload + i * frag_size, len);
+        if (sizes) sizes[i] = (uint32_t)w.n;
+        at += w.n;
+    }
+    p->pseq++;
+    return (long)n_frag;
 }
 
 // ---- PAD --------------------------------------------------------------------------------------------------------

@@ -13,6 +13,10 @@ class _EdiConfig(C.Structure):
                 ("tai_utc_offset", C.c_int32), ("start_time", C.c_int64), ("version_tag", C.c_char_p)]
 
 
+class _PftConfig(C.Structure):
+    _fields_ = [("fec", C.c_uint32), ("chunk_len", C.c_uint32)]
+
+
 def _check(rc):
     if rc < 0:
         raise TlbError("tlb error %d: %s" % (rc, lib().tlb_last_error().decode()))
@@ -32,6 +36,13 @@ def _setup(L):
     L.tlb_edi_packet_bound.restype = sz
     L.tlb_edi_packets.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
     L.tlb_edi_packets.restype = C.c_long
+    L.tlb_pft_create.argtypes = [C.POINTER(vp), C.POINTER(_PftConfig)]
+    L.tlb_pft_destroy.argtypes = [vp]
+    L.tlb_pft_destroy.restype = None
+    L.tlb_pft_bound.argtypes = [vp, sz, C.POINTER(sz)]
+    L.tlb_pft_bound.restype = sz
+    L.tlb_pft_fragments.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+    L.tlb_pft_fragments.restype = C.c_long
     L.tlb_pad_open.argtypes = [C.POINTER(vp), C.c_char_p]
     L.tlb_pad_close.argtypes = [vp]
     L.tlb_pad_close.restype = None
@@ -80,6 +91,33 @@ class EdiPacketiser:
     def close(self):
         if self._h:
             self._L.tlb_edi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+
+class PftFragmenter:
+    """The PFT layer of one EDI stream (tlb_pft_*): AF packet -> PF fragments; the PF sequence number counts packets."""
+
+    def __init__(self, fec=0, chunk_len=0):
+        self._L = _setup(lib())
+        self._h = C.c_void_p()
+        cfg = _PftConfig(fec, chunk_len)
+        _check(self._L.tlb_pft_create(C.byref(self._h), C.byref(cfg)))
+
+    def fragments(self, af_packet):
+        af = np.frombuffer(af_packet, dtype=np.uint8)
+        nmax = C.c_size_t()
+        cap = self._L.tlb_pft_bound(self._h, af.size, C.byref(nmax))
+        out = np.empty(cap, dtype=np.uint8)
+        sizes = np.zeros(nmax.value, dtype=np.uint32)
+        n = _check(self._L.tlb_pft_fragments(self._h, af.ctypes.data, af.size, out.ctypes.data, cap, sizes.ctypes.data, nmax.value))
+        ends = np.cumsum(sizes[:n])
+        return [out[e - s:e].tobytes() for s, e in zip(sizes[:n], ends)]
+
+    def close(self):
+        if self._h:
+            self._L.tlb_pft_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close

@@ -7,9 +7,12 @@
  * of the TAG items) are restated here, because src/Outputs.cpp itself needs libzmq and the socket layer; the TAI
  * offset the reference asks ClockTAI for is an argument.
  *
- * usage: edi_ref_driver TIST DELAY_MS ALIGNMENT TAI_OFFSET START_TIME VERSION_TAG FRAME_LEN IN.bin OUT.bin
+ * usage: edi_ref_driver TIST DELAY_MS ALIGNMENT TAI_OFFSET START_TIME VERSION_TAG FRAME_LEN IN.bin OUT.bin [FEC [CHUNK_LEN]]
  *   IN.bin   records of FRAME_LEN bytes + 2 x int16 (peak left, right; host byte order)
  *   OUT.bin  per frame: uint32 packet size (host byte order) + the AF packet
+ *   FEC      given (>= 0): the AF packet also goes through the reference's PFT layer (contrib/edioutput/PFT.cpp with
+ *            contrib/ReedSolomon.cpp and contrib/fec, as Sender::write does for UDP: Transport.cpp:134-139) and
+ *            OUT.bin holds, after each AF packet, uint32 fragment count and per fragment uint32 size + bytes
  */
 #include <cstdio>
 #include <cstdlib>
@@ -17,8 +20,12 @@
 #include <string>
 #include <vector>
 #include "AFPacket.h"
+#include "Log.h"
+#include "PFT.h"
 #include "TagItems.h"
 #include "TagPacket.h"
+
+Logger etiLog; /* the reference defines it in contrib/Globals.cpp, next to the remote control this driver has no use for */
 
 int main(int argc, char **argv)
 {
@@ -32,6 +39,11 @@ int main(int argc, char **argv)
     const size_t frame_len = (size_t)atol(argv[7]);
     FILE *fi = fopen(argv[8], "rb"), *fo = fopen(argv[9], "wb");
     if (!fi || !fo) return 1;
+    const int fec = argc > 10 ? atoi(argv[10]) : -1;
+    edi::configuration_t conf;
+    if (fec >= 0) conf.fec = (unsigned)fec;
+    if (argc > 11) conf.chunk_len = (unsigned)atoi(argv[11]);
+    edi::PFT pft(conf);
 
     edi::AFPacketiser afp;
     edi::TagDSTI tagDSTI;
@@ -80,6 +92,16 @@ int main(int argc, char **argv)
         const uint32_t n = (uint32_t)af.size();
         fwrite(&n, 4, 1, fo);
         fwrite(af.data(), 1, af.size(), fo);
+        if (fec >= 0) {
+            const std::vector<edi::PFTFragment> frags = pft.Assemble(af);
+            const uint32_t nf = (uint32_t)frags.size();
+            fwrite(&nf, 4, 1, fo);
+            for (const auto &f : frags) {
+                const uint32_t fs = (uint32_t)f.size();
+                fwrite(&fs, 4, 1, fo);
+                fwrite(f.data(), 1, f.size(), fo);
+            }
+        }
     }
     fclose(fi);
     fclose(fo);

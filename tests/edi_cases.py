@@ -11,6 +11,10 @@ CASES = {
 }
 
 
+# (case, fec m, chunk_len (0 = 207), packets): PFT fixtures -> tests/golden/pft_*.npz
+PFT_CASES = [("plain", 0, 0, 40), ("plain", 2, 0, 40), ("tist", 3, 0, 60), ("dmy", 1, 100, 30), ("wrap", 5, 0, 30)]
+
+
 def inputs(case, seed=7):
     n, lg = case["n"], case["frame_len"]
     f, i = np.arange(n, dtype=np.int64)[:, None], np.arange(lg, dtype=np.int64)[None, :]

@@ -108,6 +108,75 @@ def test_edi_refuses_bad_arguments():
     from odr_audioenc_b200 import TlbError, framing
     with pytest.raises(TlbError):
         framing.EdiPacketiser(tagpacket_alignment=4)
+    with pytest.raises(TlbError):
+        framing.PftFragmenter(fec=1, chunk_len=208)
+
+
+def _case_packets(name, count):
+    from odr_audioenc_b200 import framing
+    case = edi_cases.CASES[name]
+    frames, peaks = edi_cases.inputs(case)
+    e = framing.EdiPacketiser(case["tist"], case["delay_ms"], case["alignment"], case["tai"], case["start"], case["tag"])
+    return e.packets(frames[:count], case["frame_len"], peaks[:count])
+
+
+@pytest.mark.parametrize("name,fec,chunk_len,count", edi_cases.PFT_CASES, ids=["%s-m%d-k%d" % c[:3] for c in edi_cases.PFT_CASES])
+def test_pft_fragments_equal_the_reference_pft_layer(name, fec, chunk_len, count):
+    """PF fragments (TS 102 821 section 7) against fixtures from the reference's own PFT class + Reed-Solomon code
+    (contrib/edioutput/PFT.cpp, contrib/ReedSolomon.cpp, contrib/fec: oracle/_ref/edi_ref_driver), and an independent
+    check of the structure: header CRC, counters, de-interleaving back to the AF packet, RS parity = zero syndromes"""
+    from odr_audioenc_b200 import framing
+    g = np.load(os.path.join(GOLD, "pft_%s_m%d_k%d.npz" % (name, fec, chunk_len)))
+    ends = np.cumsum(g["sizes"].astype(np.int64))
+    want = [g["data"][e - s:e].tobytes() for s, e in zip(g["sizes"], ends)]
+    packets = _case_packets(name, count)
+    p = framing.PftFragmenter(fec, chunk_len)
+    got, per_packet = [], []
+    for af in packets:
+        fl = p.fragments(af)
+        per_packet.append(len(fl))
+        got += fl
+    assert per_packet == list(g["per_packet"])
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert len(got) == len(want) and not bad, "fragments differing from the reference PFT: %s" % bad[:8]
+    # structure of the first packet's fragments
+    fl, af = got[:per_packet[0]], packets[0]
+    rs = fec > 0
+    payloads = []
+    for i, f in enumerate(fl):
+        hdr = 14 if rs else 12
+        assert f[:2] == b"PF" and struct.unpack(">H", f[2:4])[0] == 0
+        assert int.from_bytes(f[4:7], "big") == i and int.from_bytes(f[7:10], "big") == len(fl)
+        plen = struct.unpack(">H", f[10:12])[0]
+        assert bool(plen & 0x8000) == rs and not plen & 0x4000 and (plen & 0x3FFF) == len(f) - hdr - 2
+        assert struct.unpack(">H", f[hdr:hdr + 2])[0] == _crc16_ccitt(f[:hdr])
+        payloads.append(f[hdr + 2:])
+    if not rs:
+        assert b"".join(payloads) == af and max(len(x) for x in payloads) <= 1400
+    else:
+        k, z = fl[0][12], fl[0][13]
+        c = (len(af) + z) // k
+        assert c * k == len(af) + z and k <= (chunk_len or 207)
+        n, size = len(fl), len(payloads[0])
+        block = bytes(payloads[j % n][j // n] for j in range(n * size))[:c * (k + 48)]   # de-interleave
+        chunks = [block[i * (k + 48):(i + 1) * (k + 48)] for i in range(c)]
+        assert (b"".join(ch[:k] for ch in chunks))[:len(af)] == af
+        # every code word (data, zero fill up to 207, parity) has zero syndromes at alpha^1 .. alpha^48
+        exp, v = [], 1
+        for _ in range(255):
+            exp.append(v)
+            v <<= 1
+            if v & 0x100:
+                v ^= 0x11d
+        log = {e: i for i, e in enumerate(exp)}
+        for ch in chunks[:3]:
+            word = ch[:k] + bytes(207 - k) + ch[k:]
+            for root in (1, 2, 17, 48):
+                acc = 0
+                for b in word:   # Horner, highest power first
+                    acc = (exp[(log[acc] + root) % 255] if acc else 0) ^ b
+                assert acc == 0
+    assert max(len(f) for f in got) <= 1400 + 14 or not rs
 
 
 class _FakePadEnc(threading.Thread):
