@@ -67,7 +67,7 @@ typedef struct tlb_batch tlb_batch;
  * max_chunk_frames = frames per kernel launch (0 = default: 75 776); device working memory is
  * about 40 kB per chunk frame (stereo, psy model 1) for each chunk slot in use.  Slots are allocated on first use
  * and sized for the path that uses them: two of max_chunk_frames on the device-resident path, three of
- * min(max_chunk_frames, 18 944) on the host-buffer path (never more than the call's n_frames). */
+ * min(max_chunk_frames, 14 208) on the host-buffer path (never more than the call's n_frames). */
 TLB_API int tlb_batch_create(tlb_batch **out, const tlb_config *cfg, int device, size_t max_chunk_frames);
 TLB_API void tlb_batch_destroy(tlb_batch *b);
 TLB_API int tlb_batch_info(const tlb_batch *b, tlb_info *info);

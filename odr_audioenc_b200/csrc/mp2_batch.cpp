@@ -45,9 +45,11 @@ constexpr int HALO = 1664;        // samples of history staged per chunk: the fi
 constexpr int HALO_PSY1 = 480, HALO_PSY2 = 1632;
 constexpr size_t DEFAULT_CHUNK = 148 * 512; // frames per launch: a multiple of the SM count, large enough to fill the
                                             // thread-per-frame kernels (k_label, k_alloc) with warps
-constexpr size_t HOST_CHUNK = 148 * 128;    // host-buffer path: smaller pieces, three in flight, so that the H2D engine
-                                            // never waits (measured end to end: 2 x 37888: 264k, 3 x 37888: 272k,
-                                            // 3 x 18944: 280k, 4 x 18944: 279k x real time; the copy alone allows 282k)
+constexpr size_t HOST_CHUNK = 148 * 96;     // host-buffer path: smaller pieces, three in flight, so that the H2D engine
+                                            // never waits (measured end to end, 10 h of config B, three interleaved
+                                            // repetitions, plain-copy ceiling of the box 281k x real time: 14 208 frames
+                                            // 281-282k, 18 944 (round 1's choice, tuned on slower kernels) 270-272k,
+                                            // 28 416 269-280k, 37 888 278-279k; two slots instead of three lose 1-20 %)
 
 int configure(const tlb_config &c, Mp2Params &P, tlb_info &I)
 {
