@@ -7,10 +7,16 @@
  * Setters return 0 on success and non-zero on error; encode / finish return the number
  * of bytes written to output_buffer.
  *
- * Differences, all on error paths: an illegal bitrate makes toolame_set_bitrate return 1
- * (the reference exit()s inside BitrateIndex, common.c:110-115); psychoacoustic models other
- * 3 is refused by toolame_set_psy_model; a missing CUDA device makes
- * toolame_encode_frame print an error and return 0.
+ * Differences, all on error paths: an illegal bitrate makes toolame_set_bitrate return 1 (the reference exit()s
+ * inside BitrateIndex, common.c:110-115); psychoacoustic model 3 is refused by toolame_set_psy_model (it reads an
+ * uninitialised array in the reference, psycho_3.c:84); 44.1 / 22.05 kHz are refused when the bitrate is set; a batch of
+ * frames that cannot be encoded (no CUDA device, or a CUDA error that survives one retry) stops the stream -- every
+ * later toolame_encode_frame returns 0 bytes, toolame_finish returns what was complete, toolame_init starts again --
+ * instead of leaving a gap in it (toolame_b200_status() in toolame_b200.h tells why).
+ *
+ * Frames are encoded lazily: the reference hands nothing back until its 4096-byte buffer has filled, so all frames
+ * pending since the last flush are encoded in one GPU batch on the call in which a flush falls due.  Bytes and return
+ * sizes are the reference's; setters are validated on the host and touch no GPU.
  */
 #ifndef TOOLAME_B200_COMPAT_H
 #define TOOLAME_B200_COMPAT_H
