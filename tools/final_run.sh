@@ -12,7 +12,7 @@ python tools/parity_sweep.py 20000 gpurun_out/parity_sweep_${TAG}_final.json > g
 SWEEP_PSY=2 python tools/parity_sweep.py 10000 gpurun_out/parity_sweep_psy2_${TAG}_final.json > gpurun_out/parity_sweep_psy2_${TAG}_final.log 2>&1
 SWEEP_PSY=0 python tools/parity_sweep.py 2000 gpurun_out/parity_sweep_psy0_${TAG}_final.json > gpurun_out/parity_sweep_psy0_${TAG}_final.log 2>&1
 python tools/probes.py > gpurun_out/probes_${TAG}.json 2>/dev/null
-tail -2 gpurun_out/parity_sweep_${TAG}_final.log gpurun_out/parity_sweep_psy2_${TAG}_final.log gpurun_out/parity_sweep_psy0_${TAG}_final.log
+tail -q -n 1 gpurun_out/parity_sweep_${TAG}_final.log gpurun_out/parity_sweep_psy2_${TAG}_final.log gpurun_out/parity_sweep_psy0_${TAG}_final.log
 python - <<PY
 import json
 for f in ("final", "final_reference", "final_cfgC", "final_cfgE"):
@@ -22,4 +22,4 @@ for f in ("final", "final_reference", "final_cfgC", "final_cfgE"):
     except Exception as e:
         print(f, "FAILED", e)
 PY
-tail -3 gpurun_out/bench_${TAG}_final.err
+tail -n 3 gpurun_out/bench_${TAG}_final.err
