@@ -75,6 +75,14 @@ def _check(rc):
     return rc
 
 
+def config_check(sample_rate, mode, bitrate, psy=1, pad_len=0):
+    """tlb_config_check: the host-side validation tlb_batch_create and toolame_set_bitrate run (no GPU is touched).
+    Returns (rc, info dict or None)."""
+    cfg, info = _Config(sample_rate, ord(mode), bitrate, psy, pad_len), _Info()
+    rc = lib().tlb_config_check(C.byref(cfg), C.byref(info))
+    return rc, ({n: getattr(info, n) for n, _ in _Info._fields_} if rc == 0 else None)
+
+
 class _Service(C.Structure):
     _fields_ = [("cfg", _Config), ("pcm", C.c_void_p), ("n_frames", C.c_size_t), ("xpad", C.c_void_p), ("out", C.c_void_p),
                 ("history_samples", C.c_size_t), ("has_next", C.c_int32)]
