@@ -179,6 +179,78 @@ def test_pft_fragments_equal_the_reference_pft_layer(name, fec, chunk_len, count
     assert max(len(f) for f in got) <= 1400 + 14 or not rs
 
 
+def _gf():
+    exp, v = [], 1
+    for _ in range(255):
+        exp.append(v)
+        v <<= 1
+        if v & 0x100:
+            v ^= 0x11d
+    return exp * 2, {e: i for i, e in enumerate(exp)}
+
+
+def _rs_fill_erasures(word, erased):
+    """word: 255 symbols (highest power first) of RS(255,207) with roots alpha^1..alpha^48, `erased` = indices whose
+    value is unknown (set to 0 in word).  Solves S_j = sum_l e_l X_l^j, j = 1..E (Gaussian elimination over GF(256))."""
+    exp, log = _gf()
+    mul = lambda a, b: exp[log[a] + log[b]] if a and b else 0
+    inv = lambda a: exp[255 - log[a]]
+    E = len(erased)
+    assert E <= 48
+    X = [exp[(254 - i) % 255] for i in erased]
+    rows = []
+    for j in range(1, E + 1):
+        syn = 0
+        for b in word:   # Horner at alpha^j
+            syn = (exp[log[syn] + j] if syn else 0) ^ b
+        rows.append([exp[(log[x] * j) % 255] for x in X] + [syn])
+    for c in range(E):
+        piv = next(r for r in range(c, E) if rows[r][c])
+        rows[c], rows[piv] = rows[piv], rows[c]
+        iv = inv(rows[c][c])
+        rows[c] = [mul(v, iv) for v in rows[c]]
+        for r in range(E):
+            if r != c and rows[r][c]:
+                f = rows[r][c]
+                rows[r] = [a ^ mul(f, b) for a, b in zip(rows[r], rows[c])]
+    out = list(word)
+    for l, i in enumerate(erased):
+        out[i] = rows[l][E]
+    return out
+
+
+@pytest.mark.parametrize("name,fec,chunk_len,count", [c for c in edi_cases.PFT_CASES if c[1] > 0],
+                         ids=["%s-m%d-k%d" % c[:3] for c in edi_cases.PFT_CASES if c[1] > 0])
+def test_pft_survives_the_loss_of_m_fragments(name, fec, chunk_len, count):
+    """what the protection is for (TS 102 821 section 7.3): with fec = m, ANY m fragments of a packet may be lost and a
+    receiver still recovers the AF packet -- encode, erase, decode with an independent erasure decoder"""
+    from odr_audioenc_b200 import framing
+    rng = np.random.RandomState(fec * 131 + count)
+    p = framing.PftFragmenter(fec, chunk_len)
+    for af in _case_packets(name, min(count, 3)):
+        fl = p.fragments(af)
+        n = len(fl)
+        k, z = fl[0][12], fl[0][13]
+        c = (len(af) + z) // k
+        payloads = [f[16:] for f in fl]
+        size = len(payloads[0])
+        for lost in (list(range(fec)), list(range(n - fec, n)), sorted(rng.choice(n, size=fec, replace=False).tolist())):
+            block, gone = bytearray(n * size), []
+            for j in range(n * size):
+                if j % n in lost:
+                    gone.append(j)
+                else:
+                    block[j] = payloads[j % n][j // n]
+            data = b""
+            for ci in range(c):
+                lo = ci * (k + 48)
+                word = list(block[lo:lo + k]) + [0] * (207 - k) + list(block[lo + k:lo + k + 48])
+                idx = [(j - lo) if j - lo < k else (j - lo - k + 207) for j in gone if lo <= j < lo + k + 48]
+                assert len(idx) <= 48, "more erasures in a code word than the code corrects"
+                data += bytes(_rs_fill_erasures(word, idx)[:k])
+            assert data[:len(af)] == af, "lost fragments %s not recovered" % lost
+
+
 class _FakePadEnc(threading.Thread):
     """stands in for ODR-PadEnc: answers each request [1, padlen] on /tmp/<ident>.padenc with [2] + record"""
 

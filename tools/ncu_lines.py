@@ -1,11 +1,10 @@
 #!/usr/bin/env python3
-"""Per-source-line summary of an ncu report: joins `ncu --page source --csv` (SASS, with executed-instruction and
-stall-sample counts) with the line table of the library's cubin (nvdisasm -g), instruction by instruction.
+"""Warp-stall samples of one kernel per CUDA source line: joins the SASS page of an ncu report
+(ncu -i REP --page source --csv --kernel-name regex:NAME) with the line table of the cubin (nvdisasm -g).
 
-usage: ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTRING [LIB.so] [TOP_N]"""
-import collections
+usage: ncu_lines.py REPORT.ncu-rep KERNEL_REGEX LIBRARY.so [TOP=40]
+"""
 import csv
-import glob
 import io
 import os
 import re
@@ -13,52 +12,52 @@ import subprocess
 import sys
 import tempfile
 
-rep, kern = sys.argv[1], sys.argv[2]
-lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(__file__), "..", "odr_audioenc_b200", "libtoolame_b200.so")
-top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(txt)))
-# several kernels may be in the report: take the first whose name matches
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and ((kern + "(") in r[1] or (kern + "<") in r[1]))
-hdr = rows[start + 1]
-ci, cs, csrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
-cti = hdr.index("Thread Instructions Executed")
-sass = []
-for r in rows[start + 2:]:
-    if not r or r[0] == "Kernel Name":
-        break
-    sass.append((r[csrc].strip(), int(r[ci]), int(r[cs]), int(r[cti])))
+def main():
+    rep, kern, so = sys.argv[1:4]
+    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+                          capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(page)))
+    hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
+    hdr = rows[hi]
+    ai, si, ni = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Source"), hdr.index("Instructions Executed")
+    sass = []
+    for r in rows[hi + 1:]:
+        if len(r) <= ai or not r[0].startswith("0x"):
+            break  # the first kernel instance only
+        sass.append((int(r[0], 16), r[si].strip(), int(r[ai]), int(r[ni])))
+    base = sass[0][0]
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, check=True, capture_output=True)
+        cubin = [f for f in os.listdir(td) if f.startswith("mp2_kernels.")][0]
+        dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cubin)], capture_output=True, text=True).stdout
+    line_of, cur, inside = {}, None, False
+    for ln in dis.splitlines():
+        if ln.startswith("//---") and ".text." in ln:
+            inside = re.search(kern, ln) is not None and "$" not in ln.split(".text.")[1].split()[0]
+        if not inside:
+            continue
+        m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', ln)
+        if m:
+            cur = int(m.group(2))
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]+)\*/", ln)
+        if m:
+            line_of[int(m.group(1), 16)] = cur
+    per_line = {}
+    total = sum(s for _, _, s, _ in sass)
+    for addr, text, s, n in sass:
+        L = line_of.get(addr - base)
+        a = per_line.setdefault(L, [0, 0])
+        a[0] += s
+        a[1] += n
+    src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "mp2_kernels.cu")).read().splitlines()
+    print("%s: %d samples, %d warp instructions" % (kern, total, sum(n for _, _, _, n in sass)))
+    for L, (s, n) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+        text = src[L - 1].strip()[:100] if L and L <= len(src) else "(library code)"
+        print("%5s %6.2f%% %10d  %s" % (L, 100.0 * s / total, n, text))
 
-with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
-    dis = ""
-    for cub in glob.glob(os.path.join(td, "*.cubin")):
-        dis += subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-sec = re.split(r"\n\s*\.section\s+\.text\.", dis)
-body = next(s for s in sec[1:] if (kern + "E") in s.split("\n", 1)[0] or (kern + "I") in s.split("\n", 1)[0])
-lines, cur = [], 0
-for ln in body.split("\n"):
-    m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
-    if m:
-        cur = int(m.group(2))
-        continue
-    m = re.match(r"\s+(/\*[0-9a-f]+\*/)?\s*([@!A-Z0-9_.]+[^;]*);", ln)
-    if m and not ln.strip().startswith("."):
-        lines.append(cur)
-if len(lines) != len(sass):
-    print("warning: %d instructions in the cubin vs %d in the report; aligning by index" % (len(lines), len(sass)))
-agg = collections.defaultdict(lambda: [0, 0, 0])
-for k, (s, n, smp, tn) in enumerate(sass):
-    a = agg[lines[k] if k < len(lines) else -1]
-    a[0] += n
-    a[1] += smp
-    a[2] += tn
-tot_i = sum(a[0] for a in agg.values()) or 1
-tot_s = sum(a[1] for a in agg.values()) or 1
-src = open(os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", "mp2_kernels.cu")).read().split("\n")
-print("kernel %s: %d warp instructions, %d stall samples" % (kern, tot_i, tot_s))
-print(" inst%  smp%  thr/inst  line  source")
-for line, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top_n]:
-    text = src[line - 1].strip()[:100] if 0 < line <= len(src) else "?"
-    print("%5.1f %5.1f %8.1f %5d  %s" % (100 * a[0] / tot_i, 100 * a[1] / tot_s, a[2] / max(a[0], 1), line, text))
+
+if __name__ == "__main__":
+    main()
