@@ -149,6 +149,11 @@ TLB_API const char *tlb_batch_kernel_name(const tlb_batch *b, int k); /* this en
 /* Measured FP64 rate of the device, TFLOP/s with mul+add = 2 flop: DFMA chains, and DMUL+DADD chains (the only
  * form this path may use: the reference is built without FMA contraction). */
 TLB_API int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops);
+/* Device self-test of the spectrum kernel's log10 (CUDA's own algorithm without the exits for zero, negative,
+ * subnormal, infinite and NaN arguments, which an energy >= 1e-20 never takes): compares bit patterns with CUDA's
+ * log10 on n values (every binade from 2^-67 to 2^60, binade edges and the reduction boundary over-sampled).  Returns
+ * the number of values that differ (0 = identical), or a negative TLB_E_* code; *first_bad = one differing value. */
+TLB_API long long tlb_selftest_log10(int device, unsigned long long n, double *first_bad);
 
 /* Pinned host memory for pcm / out buffers. */
 TLB_API void *tlb_host_alloc(size_t bytes);

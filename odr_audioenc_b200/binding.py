@@ -65,6 +65,8 @@ def lib():
         L.toolame_encode_frame.argtypes = [vp, vp, sz, vp, sz]
         L.toolame_finish.argtypes = [vp, sz]
         L.tlb_config_check.argtypes = [C.POINTER(_Config), C.POINTER(_Info)]
+        L.tlb_selftest_log10.argtypes = [i32, C.c_ulonglong, C.POINTER(C.c_double)]
+        L.tlb_selftest_log10.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -81,6 +83,15 @@ def config_check(sample_rate, mode, bitrate, psy=1, pad_len=0):
     cfg, info = _Config(sample_rate, ord(mode), bitrate, psy, pad_len), _Info()
     rc = lib().tlb_config_check(C.byref(cfg), C.byref(info))
     return rc, ({n: getattr(info, n) for n, _ in _Info._fields_} if rc == 0 else None)
+
+
+def selftest_log10(n=1 << 28, device=0):
+    """tlb_selftest_log10: values (of n) on which the spectrum kernel's log10 differs from CUDA's log10, and one of them"""
+    first = C.c_double(0.0)
+    bad = lib().tlb_selftest_log10(device, n, C.byref(first))
+    if bad < 0:
+        raise TlbError("tlb error %d: %s" % (bad, lib().tlb_last_error().decode()))
+    return bad, first.value
 
 
 class _Service(C.Structure):

@@ -569,6 +569,14 @@ int tlb_fp64_peak(int device, double *dfma_tflops, double *dmul_dadd_tflops)
     return 0;
 }
 
+long long tlb_selftest_log10(int device, unsigned long long n, double *first_bad)
+{
+    CU(cudaSetDevice(device));
+    const long long bad = mp2_selftest_log10(n, first_bad);
+    if (bad < 0) return fail(TLB_E_CUDA, "log10 self-test could not run");
+    return bad;
+}
+
 void *tlb_host_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -79,6 +79,7 @@ extern const char *const MP2_KERNEL_NAMES[MP2_N_KERNELS];
 
 // Measured FP64 rate of the device in TFLOP/s (mul+add counted as 2): DFMA chains, or DMUL+DADD chains.
 double mp2_fp64_probe(bool fma, cudaStream_t stream);
+long long mp2_selftest_log10(unsigned long long n, double *first_bad);
 
 // Gain correction in place + per-frame peak levels of interleaved s16 PCM (src/odr-audioenc.cpp:1020-1055).
 void mp2_launch_gain_peak(int16_t *d_pcm, long n_frames, int nch, double linear_gain, int16_t *d_peaks, cudaStream_t stream);
