@@ -20,6 +20,7 @@ def main():
                           capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(page)))
     hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
+    full_name = next(r[1] for r in rows if r and r[0] == "Kernel Name")   # demangled, template arguments included
     hdr = rows[hi]
     ai, si, ni = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Source"), hdr.index("Instructions Executed")
     sass = []
@@ -33,14 +34,18 @@ def main():
         cubin = [f for f in os.listdir(td) if f.startswith("mp2_kernels.")][0]
         dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cubin)], capture_output=True, text=True).stdout
     line_of, cur, inside = {}, None, False
+    demangled = {}
     for ln in dis.splitlines():
         if ln.startswith("//---") and ".text." in ln:
-            inside = re.search(kern, ln) is not None and "$" not in ln.split(".text.")[1].split()[0]
+            sym = ln.split(".text.")[1].split()[0]
+            if sym not in demangled:   # the instance of a template that the report holds, not its siblings
+                demangled[sym] = subprocess.run(["cu++filt", sym], capture_output=True, text=True).stdout.strip()
+            inside = "$" not in sym and demangled[sym].replace("void ", "") == full_name.replace("void ", "")
         if not inside:
             continue
         m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', ln)
-        if m:
-            cur = int(m.group(2))
+        if m:   # lines of other files (CUDA's headers: intrinsics, atomics) are shown under the header's name
+            cur = int(m.group(2)) if m.group(1) == "mp2_kernels.cu" else "%s:%s" % (m.group(1), m.group(2))
             continue
         m = re.match(r"\s+/\*([0-9a-f]+)\*/", ln)
         if m:
@@ -55,8 +60,8 @@ def main():
     src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "mp2_kernels.cu")).read().splitlines()
     print("%s: %d samples, %d warp instructions" % (kern, total, sum(n for _, _, _, n in sass)))
     for L, (s, n) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
-        text = src[L - 1].strip()[:100] if L and L <= len(src) else "(library code)"
-        print("%5s %6.2f%% %10d  %s" % (L, 100.0 * s / total, n, text))
+        text = src[L - 1].strip()[:100] if isinstance(L, int) and L <= len(src) else "(%s)" % (L or "no line")
+        print("%5s %6.2f%% %10d  %s" % (L if isinstance(L, int) else "", 100.0 * s / total, n, text))
 
 
 if __name__ == "__main__":
