@@ -8,8 +8,8 @@ python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_final.json 2> gp
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${TAG}_final_reference.json 2>> gpurun_out/bench_${TAG}_final.err
 python bench.py --config C --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_final_cfgC.json 2>> gpurun_out/bench_${TAG}_final.err
 python bench.py --config E --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_final_cfgE.json 2>> gpurun_out/bench_${TAG}_final.err
-python tools/parity_sweep.py 20000 gpurun_out/parity_sweep_${TAG}_final.json > gpurun_out/parity_sweep_${TAG}_final.log 2>&1
-SWEEP_PSY=2 python tools/parity_sweep.py 10000 gpurun_out/parity_sweep_psy2_${TAG}_final.json > gpurun_out/parity_sweep_psy2_${TAG}_final.log 2>&1
+python tools/parity_sweep.py ${SWEEP_N:-20000} gpurun_out/parity_sweep_${TAG}_final.json > gpurun_out/parity_sweep_${TAG}_final.log 2>&1
+SWEEP_PSY=2 python tools/parity_sweep.py ${SWEEP_N2:-10000} gpurun_out/parity_sweep_psy2_${TAG}_final.json > gpurun_out/parity_sweep_psy2_${TAG}_final.log 2>&1
 SWEEP_PSY=0 python tools/parity_sweep.py 2000 gpurun_out/parity_sweep_psy0_${TAG}_final.json > gpurun_out/parity_sweep_psy0_${TAG}_final.log 2>&1
 python tools/probes.py > gpurun_out/probes_${TAG}.json 2>/dev/null
 tail -q -n 1 gpurun_out/parity_sweep_${TAG}_final.log gpurun_out/parity_sweep_psy2_${TAG}_final.log gpurun_out/parity_sweep_psy0_${TAG}_final.log
