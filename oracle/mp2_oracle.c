@@ -397,7 +397,7 @@ static void psy1_threshold(const psy1_lines *p, int fq, int tone, int noise, int
 void mp2o_psy1_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame,
                      const uint8_t scalar_pre[3][32], double smr[32], double ltmin[32], double spike[32])
 {
-    static psy1_lines P; /* oracle is single-threaded test code */
+    static _Thread_local psy1_lines P; /* big working set: static, one per thread */
     double xr[1024], energy[513];
     int fq = c->psy_freq, tone, noise;
     psy1_make_map(fq, P.map);
@@ -481,9 +481,9 @@ static void psy2_spectrum(const int16_t *pcm, int nch, int ch, long block, p2_sp
  * (psycho_2.c:322-326). */
 void mp2o_psy2_frame(const mp2o_cfg *c, const int16_t *pcm, int ch, long frame, double smr[32])
 {
-    static mp2_psy2_tables T;
-    static double T_for = 0;
-    static p2_spec S[3];
+    static _Thread_local mp2_psy2_tables T;
+    static _Thread_local double T_for = 0;
+    static _Thread_local p2_spec S[3];
     const double nmt = 5.5, LN_TO_LOG10 = 0.2302585093;
     double sfreq = (double)c->fs_hz; /* (FLOAT) s_freq[version][idx] * 1000 */
     if (T_for != sfreq) { mp2_psy2_init(&T, sfreq); T_for = sfreq; }
@@ -719,7 +719,7 @@ typedef struct {
 
 static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint8_t *xpad_rec, frame_out *fo, mp2o_tap *tap)
 {
-    static mp2o_tap T; /* big; oracle is single-threaded */
+    static _Thread_local mp2o_tap T; /* big: static, one per thread */
     mp2o_tap *t = tap ? tap : &T;
     memset(t, 0, sizeof *t);
     int nch = c->nch, sblimit = c->sblimit;
@@ -727,7 +727,7 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
     /* ref: toolame.c:292-302 */
     int adb = 8 * c->lg_frame - (c->dab_ext * 8 + (xpad_len ? xpad_len : 2) * 8);
 
-    static double jsamp[36][32];
+    static _Thread_local double jsamp[36][32];
     for (int ch = 0; ch < nch; ch++) {
         mp2o_filterbank_frame(pcm, nch, ch, n, t->sb_sample[ch]);
         scalefactors(t->sb_sample[ch], sblimit, t->scalar_pre[ch]);
@@ -741,7 +741,7 @@ static void encode_one(const mp2o_cfg *c, const int16_t *pcm, long n, const uint
     /* ref: toolame.c:361-452 (psy model switch); models 1 and 2 are restated */
     for (int ch = 0; ch < nch; ch++) {
         if (c->psy == 0) { /* ref: psycho_0.c:27-69: SMR from the smallest scalefactor index and the subband's lowest ATH */
-            static double ath_min[32], ath_for = 0;
+            static _Thread_local double ath_min[32], ath_for = 0;
             if (ath_for != (double)c->fs_hz) { mp2_psy0_init(ath_min, (double)c->fs_hz); ath_for = (double)c->fs_hz; }
             for (int sb = 0; sb < 32; sb++) {
                 int mn = t->scalar_pre[ch][0][sb];
@@ -865,7 +865,7 @@ int mp2o_encode(const mp2o_cfg *c, const int16_t *pcm, long n_frames_total, long
                 const uint8_t *xpad, uint8_t *out, mp2o_tap *taps)
 {
     if (c->psy < 0 || c->psy > 2) return -1;
-    static frame_out fo;
+    static _Thread_local frame_out fo;
     for (long n = f0; n < f1 + 1 && n < n_frames_total; n++) {
         const uint8_t *rec = xpad ? xpad + (size_t)n * (c->pad_len + 1) : NULL;
         encode_one(c, pcm, n, rec, &fo, (taps && n < f1) ? &taps[n - f0] : NULL);
