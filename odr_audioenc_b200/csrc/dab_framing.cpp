@@ -373,6 +373,8 @@ int tlb_pad_open(tlb_pad **out, const char *ident)
 {
     if (!out || !ident || !*ident) return tlb_fail(TLB_E_ARG, "NULL argument");
     *out = nullptr;
+    if (std::strlen(ident) > sizeof(((struct sockaddr_un *)nullptr)->sun_path) - sizeof("/tmp/.audioenc"))
+        return tlb_fail(TLB_E_ARG, "PAD identifier too long for a socket path"); // (would be cut short silently)
     tlb_pad *p = new (std::nothrow) tlb_pad();
     if (!p) return tlb_fail(TLB_E_ARG, "out of memory");
     p->ident = ident;

@@ -285,6 +285,8 @@ def test_pad_socket_protocol():
     from odr_audioenc_b200 import TlbError, framing
     ident = "tlbtest%d" % os.getpid()
     pad_len = 23
+    with pytest.raises(TlbError):   # a name that does not fit a socket path is refused, not cut short
+        framing.PadSocket("x" * 120)
     rec_a = bytes(range(pad_len - 8)) + b"\xAA" * 8 + bytes([8])          # 8 bytes used
     rec_b = bytes(pad_len - 2) + b"\x40\x00" + bytes([2])                   # F-PAD only
     p = framing.PadSocket(ident)
